@@ -1,0 +1,327 @@
+"""Host planner + launcher for the grid->region aggregation kernels.
+
+Python here is plumbing only: it factorises region labels, keeps a content-keyed
+plan cache (the analogue of ``toolz.memoize`` at
+``/root/reference/climate_toolbox/aggregations/aggregations.py:127``), owns device
+buffers through torch, and calls the C-ABI in ``libctb.so``.  All arithmetic of
+the path runs in the CUDA kernels; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+from collections import OrderedDict
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _native as N
+
+__all__ = ["Plan", "GridSpec", "get_plan", "aggregate_device", "aggregate_host",
+           "materialize_deferred", "default_device", "launch_count"]
+
+_NP2CTB = {np.dtype("float32"): N.F32, np.dtype("float64"): N.F64}
+_T2CTB = {torch.float32: N.F32, torch.float64: N.F64}
+_KIND = {"identity": N.TR_IDENTITY, "poly": N.TR_POLY, "edd": N.TR_EDD, "gdd": N.TR_GDD}
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("climate_toolbox_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback for the aggregation path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def launch_count():
+    return int(N.lib().ctb_launch_count())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class GridSpec:
+    """Coordinate labels of the spatial axes + where each label physically lives."""
+
+    def __init__(self, lat, lon, lat_phys=None, lon_phys=None, nlat_phys=None, nlon_phys=None):
+        self.lat = np.ascontiguousarray(lat, dtype=np.float64)
+        self.lon = np.ascontiguousarray(lon, dtype=np.float64)
+        self.lat_phys = None if lat_phys is None else np.ascontiguousarray(lat_phys, dtype=np.int32)
+        self.lon_phys = None if lon_phys is None else np.ascontiguousarray(lon_phys, dtype=np.int32)
+        self.nlat_phys = int(nlat_phys if nlat_phys is not None else len(self.lat))
+        self.nlon_phys = int(nlon_phys if nlon_phys is not None else len(self.lon))
+
+    def digest(self, h):
+        for a in (self.lat, self.lon, self.lat_phys, self.lon_phys):
+            h.update(b"-" if a is None else a.tobytes())
+        h.update(np.array([self.nlat_phys, self.nlon_phys]).tobytes())
+
+
+class Plan:
+    """Owns a ``ctb_plan*`` (region-sorted CSR + staging bundles on the device)."""
+
+    def __init__(self, handle, device, region_labels, n_rows):
+        self._h = handle
+        self.device = device
+        self.region_labels = region_labels
+        self.n_rows = n_rows
+        info = N.PlanInfo()
+        N.check(N.lib().ctb_plan_get_info(self._h, C.byref(info)))
+        self.info = info.as_dict()
+        self._tix_cache = {}
+
+    R = property(lambda s: s.info["n_regions"])
+
+    def _host_array(self, fn, n, dtype, ptr):
+        out = np.empty(n, dtype=dtype)
+        N.check(getattr(N.lib(), fn)(self._h, ptr(out)))
+        return out
+
+    def row_cells(self):
+        """Physical flat gridcell index of every weights row (the index map)."""
+        return self._host_array("ctb_plan_row_cells", self.n_rows, np.int32, _ip)
+
+    def row_weights(self):
+        return self._host_array("ctb_plan_row_weights", self.n_rows, np.float64, _dp)
+
+    def den(self):
+        return self._host_array("ctb_plan_den", self.R, np.float64, _dp)
+
+    def algorithmic_bytes(self, T, n_in, elem_bytes, n_out):
+        """T*(n_in*s_in*U + n_out*8*R) + 12*nnz."""
+        i = self.info
+        return T * (n_in * elem_bytes * i["n_cells_distinct"] + n_out * 8 * i["n_regions"]) \
+            + 12 * i["nnz"]
+
+    def time_index_device(self, tix):
+        if tix is None:
+            return None
+        key = hashlib.sha1(tix.tobytes()).hexdigest()
+        if key not in self._tix_cache:
+            if len(self._tix_cache) > 16:
+                self._tix_cache.clear()
+            self._tix_cache[key] = torch.as_tensor(tix.astype(np.int32), device=self.device)
+        return self._tix_cache[key]
+
+    def close(self):
+        if self._h:
+            N.lib().ctb_plan_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_PLAN_CACHE: "OrderedDict[str, Plan]" = OrderedDict()
+_PLAN_CACHE_SIZE = 8
+
+
+def region_codes(labels):
+    """Sorted-unique region labels and the code of every row (NaN label -> -1);
+    ``xarray.groupby`` orders groups like ``pd.factorize(sort=True)``."""
+    codes, uniques = pd.factorize(np.asarray(labels), sort=True)
+    return codes.astype(np.int32), np.asarray(uniques)
+
+
+def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4, device=None,
+             smem_budget=0, cache=True):
+    """Build (or fetch) the device plan for (grid, weights[lat, lon, agglev, aggwt, backup])."""
+    device = device or default_device()
+    for col in ("lat", "lon", agglev, aggwt, backup_aggwt):
+        if col not in weights:
+            raise KeyError(col)
+    row_lat = np.ascontiguousarray(weights["lat"].values, dtype=np.float64)
+    row_lon = np.ascontiguousarray(weights["lon"].values, dtype=np.float64)
+    wp = np.ascontiguousarray(weights[aggwt].values, dtype=np.float64)
+    wb = np.ascontiguousarray(weights[backup_aggwt].values, dtype=np.float64)
+    codes, labels = region_codes(weights[agglev].values)
+    codes = np.ascontiguousarray(codes)
+
+    h = hashlib.sha1()
+    grid.digest(h)
+    for a in (row_lat, row_lon, wp, wb, codes):
+        h.update(a.tobytes())
+    h.update(repr((stage_bytes, smem_budget, str(device), len(labels))).encode())
+    key = h.hexdigest()
+    if cache and key in _PLAN_CACHE:
+        _PLAN_CACHE.move_to_end(key)
+        return _PLAN_CACHE[key]
+
+    opts = N.PlanOpts()
+    opts.stage_bytes_per_cell_day = int(stage_bytes)
+    opts.smem_budget_bytes = int(smem_budget)
+    handle = C.c_void_p()
+    bad_row, bad_axis = C.c_int64(-1), C.c_int32(-1)
+    rc = N.lib().ctb_plan_build(
+        _dp(grid.lat), len(grid.lat), _ip(grid.lat_phys), grid.nlat_phys,
+        _dp(grid.lon), len(grid.lon), _ip(grid.lon_phys), grid.nlon_phys,
+        _dp(row_lat), _dp(row_lon), _ip(codes), _dp(wp), _dp(wb), len(row_lat), len(labels),
+        C.byref(opts), device.index or 0, C.byref(handle), C.byref(bad_row), C.byref(bad_axis))
+    N.check(rc)
+    plan = Plan(handle, device, labels, len(row_lat))
+    if cache:
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def _params_array(kind, params):
+    a = np.ascontiguousarray(params, dtype=np.float64)
+    return a, (_dp(a) if a.size else None)
+
+
+def _stream_ptr(device, stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream(device)
+    return C.c_void_p(s.cuda_stream)
+
+
+def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", params=(), n_out=1,
+                     variant=N.VARIANT_AUTO, out=None, out_ld=0, stream=None, workspace=None):
+    """Launch the fused kernel on device-resident inputs.
+
+    ``x0`` / ``x1``: contiguous CUDA tensors (f32/f64).  ``tix``: numpy int array of
+    physical time positions or None.  Returns ``out`` ([n_out, R, T] float64 CUDA).
+    """
+    dev = plan.device
+    if x0.device != dev or not x0.is_contiguous():
+        raise ValueError("input must be a contiguous tensor on {}".format(dev))
+    if x0.dtype not in _T2CTB:
+        raise TypeError("unsupported dtype {}".format(x0.dtype))
+    if x1 is not None and (x1.dtype != x0.dtype or x1.shape != x0.shape):
+        raise ValueError("the two inputs must agree in dtype and shape")
+    if out is None:
+        out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
+    L = N.lib()
+    ws_bytes = L.ctb_aggregate_workspace_bytes(plan._h, T, n_out) \
+        if variant != N.VARIANT_DIRECT and layout == N.LAYOUT_TIME_MAJOR else 0
+    if ws_bytes and (workspace is None or workspace.numel() * 8 < ws_bytes):
+        workspace = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
+    tix_d = plan.time_index_device(tix)
+    pa, pp = _params_array(kind, params)
+    rc = L.ctb_aggregate(
+        plan._h, C.c_void_p(x0.data_ptr()), C.c_void_p(x1.data_ptr()) if x1 is not None else None,
+        _T2CTB[x0.dtype], layout, int(stride),
+        C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
+        _KIND[kind], pp, int(pa.size), int(n_out), C.c_void_p(out.data_ptr()), int(out_ld),
+        C.c_void_p(workspace.data_ptr()) if workspace is not None else None,
+        int(workspace.numel() * 8) if workspace is not None else 0, int(variant),
+        _stream_ptr(dev, stream))
+    N.check(rc)
+    return out
+
+
+def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(), n_out=1,
+                   variant=N.VARIANT_AUTO, chunk_bytes=256 << 20):
+    """Host (numpy) inputs: time-chunked H2D copies double-buffered against the kernel.
+
+    ``xs``: list of 1 or 2 C-contiguous numpy arrays viewed as 2-D
+    (TIME_MAJOR: [t_phys, stride]; CELL_MAJOR: [ncell, stride]).  Pinned arrays copy
+    asynchronously at PCIe speed; pageable ones go through the driver's staging.
+    Returns a CUDA tensor [n_out, R, T].
+    """
+    dev = plan.device
+    out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
+    if T == 0 or plan.R == 0:
+        return out
+    ts = [torch.from_numpy(x) for x in xs]
+    if layout == N.LAYOUT_CELL_MAJOR:
+        d = [t.to(dev, non_blocking=True) for t in ts]
+        return aggregate_device(plan, d[0], d[1] if len(d) > 1 else None, layout, stride, tix, T,
+                                kind, params, n_out, variant, out=out)
+    # TIME_MAJOR: chunk over output days; each chunk needs planes [lo, hi] of the input
+    tix_full = np.arange(T, dtype=np.int64) if tix is None else np.asarray(tix, dtype=np.int64)
+    plane_bytes = xs[0].shape[1] * xs[0].dtype.itemsize * len(xs)
+    days = max(32, int(chunk_bytes // max(plane_bytes, 1)) // 32 * 32)
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(dev)
+    copy_stream.wait_stream(main)
+    bufs, free_ev = {}, {}
+    ws = None
+    ws_bytes = N.lib().ctb_aggregate_workspace_bytes(plan._h, min(days, T), n_out)
+    if ws_bytes:
+        ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
+    for ci, t0 in enumerate(range(0, T, days)):
+        t1 = min(T, t0 + days)
+        sub = tix_full[t0:t1]
+        lo, hi = int(sub.min()), int(sub.max()) + 1
+        slot = ci % 2
+        with torch.cuda.stream(copy_stream):
+            if slot in free_ev:
+                copy_stream.wait_event(free_ev[slot])
+            cur = []
+            for k, t in enumerate(ts):
+                need = (hi - lo, t.shape[1])
+                b = bufs.get((slot, k))
+                if b is None or b.shape[0] < need[0]:
+                    b = torch.empty((max(need[0], days + 8), t.shape[1]), dtype=t.dtype, device=dev)
+                    b.record_stream(main)
+                    bufs[(slot, k)] = b
+                b[: need[0]].copy_(t[lo:hi], non_blocking=True)
+                cur.append(b)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main.wait_event(ready)
+        rel = None if (tix is None) else (sub - lo)
+        if tix is not None and np.array_equal(rel, np.arange(t1 - t0)):
+            rel = None
+        aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, stride, rel,
+                         t1 - t0, kind, params, n_out, variant,
+                         out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        free_ev[slot] = ev
+    return out
+
+
+class _OffsetOut:
+    """Pointer view of ``out[:, :, t0:]`` for a time-chunked launch (out_ld = total T)."""
+
+    def __init__(self, base, t0):
+        self._p = base.data_ptr() + 8 * t0
+        self.base = base
+
+    def data_ptr(self):
+        return self._p
+
+
+# ---------------------------------------------------------------------------
+# deferred variables (`.values` of a transformed / reindexed variable)
+# ---------------------------------------------------------------------------
+def _to_device(v, dev):
+    """Materialise a (non-deferred) Variable on the device with its lazy takes applied."""
+    a = v.physical
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    t = t.to(dev)
+    for ax, d in enumerate(v.dims):
+        if d in v.takes:
+            t = t.index_select(ax, torch.as_tensor(v.takes[d], device=dev))
+    return t.contiguous()
+
+
+def materialize_deferred(var):
+    """Evaluate a deferred pointwise transform with the CUDA kernel (ctb_transform)."""
+    d = var.deferred
+    dev = default_device()
+    if d.kind == "reindex":
+        return d.params[0]()  # closure built by aggregations._pointwise_reindex
+    srcs = [_to_device(s, dev) for s in d.sources]
+    if srcs[0].dtype not in _T2CTB:
+        srcs = [s.to(torch.float64) for s in srcs]
+    n = srcs[0].numel()
+    out = torch.empty((1,) + tuple(srcs[0].shape), dtype=torch.float64, device=dev)
+    pa, pp = _params_array(d.kind, d.params)
+    rc = N.lib().ctb_transform(
+        C.c_void_p(srcs[0].data_ptr()), C.c_void_p(srcs[1].data_ptr()) if len(srcs) > 1 else None,
+        _T2CTB[srcs[0].dtype], n, _KIND[d.kind], pp, int(pa.size), 1,
+        C.c_void_p(out.data_ptr()), _stream_ptr(dev))
+    N.check(rc)
+    return out[0].cpu().numpy()

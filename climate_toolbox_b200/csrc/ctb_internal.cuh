@@ -1,0 +1,150 @@
+// Internal declarations shared by the translation units of libctb.so.
+// Public surface: include/ctb.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "ctb.h"
+
+// ---------------------------------------------------------------- errors ---
+void ctb_set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_ctb_launches;
+
+#define CTB_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      ctb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,    \
+                    __LINE__);                                                           \
+      return CTB_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define CTB_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    g_ctb_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    CTB_CUDA(cudaGetLastError());                                                        \
+  } while (0)
+
+// ------------------------------------------------------------- constants ---
+constexpr int CTB_TB = 32;             // days per staging tile (one warp of lanes)
+constexpr int CTB_S = CTB_TB + 1;      // smem row stride in elements: odd => conflict-free
+constexpr int CTB_PIECE = 4;           // gridcells per staged piece (16 B of f32)
+constexpr int CTB_STAGE_THREADS = 256; // 8 warps: each stages 4 days x 8 pieces per step
+
+// -------------------------------------------------------------- the plan ---
+struct ctb_plan {
+  int device = 0;
+  int32_t R = 0;
+  int64_t n_rows = 0, nnz = 0, ncell = 0;
+  int32_t nlat_phys = 0, nlon_phys = 0;
+
+  // K0 products (device): region-sorted CSR over kept rows
+  int32_t* d_row_cell = nullptr;  // [n_rows]  physical flat cell of every weights row
+  int32_t* d_row_ptr = nullptr;   // [R+1]
+  int32_t* d_col = nullptr;       // [nnz]
+  double* d_w = nullptr;          // [nnz]
+  double* d_den = nullptr;        // [R]
+
+  // staging bundles (device)
+  int32_t n_bundles = 0, n_segments = 0;
+  int32_t* d_b_piece_ptr = nullptr;  // [n_bundles+1] -> d_pieces
+  int32_t* d_pieces = nullptr;       // global piece index (cell / 4), ascending per bundle
+  int32_t* d_b_seg_ptr = nullptr;    // [n_bundles+1] -> segments
+  int32_t* d_seg_target = nullptr;   // >=0: region row of `out`; <0: ~scratch_slot
+  int32_t* d_seg_ent_ptr = nullptr;  // [n_segments+1] -> entries
+  double* d_ent_w = nullptr;         // [n_entries]
+  uint16_t* d_ent_loc = nullptr;     // [n_entries] local staged cell
+  // regions split over several bundles: out[r] = sum(scratch[slot0..slot1)) / den[r]
+  int32_t n_split = 0, n_scratch = 0;
+  int32_t* d_split_region = nullptr;  // [n_split]
+  int32_t* d_split_slot_ptr = nullptr;  // [n_split+1]
+
+  // host mirrors for queries
+  std::vector<int32_t> h_row_cell;
+  std::vector<double> h_row_w;
+  std::vector<double> h_den;
+  ctb_plan_info info{};
+};
+
+// ------------------------------------------------- gridcell transforms -----
+struct CtbTr {
+  double a[8];  // thresholds / offset
+  int ip[4];    // integer powers (POLY)
+};
+
+__device__ __forceinline__ double ctb_ipow(double d, int p) {
+  // integer power by squaring; p is warp-uniform
+  double r = 1.0, b = d;
+  int n = p < 0 ? -p : p;
+  while (n) {
+    if (n & 1) r *= b;
+    b *= b;
+    n >>= 1;
+  }
+  return p < 0 ? 1.0 / r : r;
+}
+
+// Snyder exceedance degree days, transformations.py:69-89.
+// cos(asin(s)) is evaluated as sqrt((1-s)(1+s)) (identical on [-1,1], no
+// cancellation); asin(|s|>1) stays NaN as in numpy.
+__device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double e) {
+  double r;
+  if (tmin < e) {
+    if (tmax > e) {
+      const double s = (e - M) / W;
+      const double th = asin(s);
+      const double c = sqrt(fmax((1.0 - s) * (1.0 + s), 0.0));
+      r = ((M - e) * (1.5707963267948966 - th) + W * c) / 3.141592653589793;
+    } else {
+      r = 0.0;
+    }
+  } else {
+    r = M - e;
+  }
+  return r;
+}
+
+template <int KIND, int NOUT>
+__device__ __forceinline__ void ctb_apply(const CtbTr& P, double x0, double x1, double (&f)[NOUT]) {
+  if constexpr (KIND == CTB_TR_IDENTITY) {
+    f[0] = x0;
+  } else if constexpr (KIND == CTB_TR_POLY) {
+    const double d = x0 - P.a[0];
+    bool chain = true;
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) chain = chain && (P.ip[j] == j + 1);
+    if (chain) {  // powers 1..NOUT from one read (config 3)
+      double p = d;
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) {
+        f[j] = p;
+        p *= d;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) f[j] = ctb_ipow(d, P.ip[j]);
+    }
+  } else if constexpr (KIND == CTB_TR_EDD) {
+    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2;
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) f[j] = ctb_edd(x0, x1, M, W, P.a[j]);
+  } else {  // GDD
+    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2;
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j)
+      f[j] = ctb_edd(x0, x1, M, W, P.a[2 * j]) - ctb_edd(x0, x1, M, W, P.a[2 * j + 1]);
+  }
+}
+
+static inline int ctb_tr_nin(int kind) { return (kind == CTB_TR_EDD || kind == CTB_TR_GDD) ? 2 : 1; }
+
+// host: validate + pack transform params. returns CTB_OK or error.
+int ctb_pack_transform(int transform, const double* params, int n_params, int n_out, CtbTr* out);

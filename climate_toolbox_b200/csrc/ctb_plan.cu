@@ -1,0 +1,554 @@
+// K0: one-time plan build.
+//
+//  device part  -- exact float64 label -> gridcell index, per-row fallback weight,
+//                  stable region sort, CSR row pointers, per-region denominators
+//                  (replaces climate_toolbox/aggregations/aggregations.py:24-27, 64-73, 79)
+//  host part    -- the planner: groups spatially adjacent regions into staging
+//                  "bundles" whose gridcell footprint fits one shared-memory tile,
+//                  and splits regions that are larger than a tile.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <numeric>
+
+#include "ctb_internal.cuh"
+
+// ------------------------------------------------------------ error state ---
+static thread_local std::string g_err;
+std::atomic<int64_t> g_ctb_launches{0};
+
+void ctb_set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+extern "C" const char* ctb_last_error(void) { return g_err.c_str(); }
+extern "C" int ctb_version(void) { return CTB_VERSION; }
+extern "C" int64_t ctb_launch_count(void) { return g_ctb_launches.load(); }
+
+// ------------------------------------------------------------- K0 kernels ---
+// Exact-equality lookup of `v` in ascending `sorted[n]`; returns position in the
+// ORIGINAL label order via order[], or -1.  NaN never matches; -0.0 == 0.0.
+__device__ __forceinline__ int k0_find(const double* __restrict__ sorted,
+                                       const int32_t* __restrict__ order, int n, double v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sorted[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return (lo < n && sorted[lo] == v) ? order[lo] : -1;
+}
+
+__global__ void k0_match_kernel(const double* __restrict__ slat, const int32_t* __restrict__ olat,
+                                int nlat, const int32_t* __restrict__ lat_phys,
+                                const double* __restrict__ slon, const int32_t* __restrict__ olon,
+                                int nlon, const int32_t* __restrict__ lon_phys, int nlon_phys,
+                                const double* __restrict__ row_lat,
+                                const double* __restrict__ row_lon,
+                                const double* __restrict__ wp, const double* __restrict__ wb,
+                                int64_t n_rows, int32_t* __restrict__ row_cell,
+                                double* __restrict__ row_w, unsigned long long* bad) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n_rows) return;
+  const int i = k0_find(slat, olat, nlat, row_lat[k]);
+  const int j = k0_find(slon, olon, nlon, row_lon[k]);
+  if (i < 0 || j < 0) {
+    // first offending row wins; low bit = axis (0 lat, 1 lon)
+    atomicMin(bad, ((unsigned long long)k << 1) | (i < 0 ? 0ull : 1ull));
+    row_cell[k] = -1;
+  } else {
+    const int pi = lat_phys ? lat_phys[i] : i;
+    const int pj = lon_phys ? lon_phys[j] : j;
+    row_cell[k] = pi * nlon_phys + pj;
+  }
+  const double p = wp[k];
+  row_w[k] = (p > 0) ? p : wb[k];  // NaN, 0 and negatives fall back (aggregations.py:73)
+}
+
+// row_ptr[r] = first sorted position whose key >= r
+__global__ void k0_rowptr_kernel(const uint32_t* __restrict__ keys, int64_t n, int32_t R,
+                                 int32_t* __restrict__ row_ptr) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < (uint32_t)r) lo = mid + 1; else hi = mid;
+  }
+  row_ptr[r] = (int32_t)lo;
+}
+
+// den[r] = sum of nan->0(w) over the region's rows in stable (original) order.
+__global__ void k0_den_kernel(const int32_t* __restrict__ row_ptr,
+                              const int32_t* __restrict__ sorted_row,
+                              const double* __restrict__ row_w, int32_t R,
+                              double* __restrict__ den) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  double s = 0.0;
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+    const double w = row_w[sorted_row[k]];
+    if (w == w) s += w;
+  }
+  den[r] = s;
+}
+
+// ------------------------------------------------------------ host planner ---
+namespace {
+
+struct Region {
+  int32_t r;
+  int32_t e0, e1;  // range in kept-CSR
+  uint64_t hkey;   // Hilbert index of the centroid
+};
+
+// Hilbert curve index of (x, y) in an n x n grid (n power of two).
+uint64_t hilbert_xy2d(uint32_t n, uint32_t x, uint32_t y) {
+  uint64_t d = 0;
+  for (uint32_t s = n / 2; s > 0; s /= 2) {
+    const uint32_t rx = (x & s) > 0, ry = (y & s) > 0;
+    d += (uint64_t)s * s * ((3 * rx) ^ ry);
+    if (ry == 0) {
+      if (rx == 1) { x = n - 1 - x; y = n - 1 - y; }
+      std::swap(x, y);
+    }
+  }
+  return d;
+}
+
+struct BundleBuilder {
+  // flat outputs
+  std::vector<int32_t> b_piece_ptr{0}, pieces, b_seg_ptr{0}, seg_target, seg_ent_ptr{0};
+  std::vector<double> ent_w;
+  std::vector<uint16_t> ent_loc;
+  int32_t max_cells = 0;
+
+  // current bundle under construction
+  std::vector<int32_t> cur_pieces;  // unsorted, unique
+  struct Seg { int32_t target; std::vector<int32_t> cols; std::vector<double> ws; };
+  std::vector<Seg> cur_segs;
+
+  void close() {
+    if (cur_segs.empty()) return;
+    std::sort(cur_pieces.begin(), cur_pieces.end());
+    // LPT order: longest segments first (warps fetch segments dynamically)
+    std::stable_sort(cur_segs.begin(), cur_segs.end(),
+                     [](const Seg& a, const Seg& b) { return a.cols.size() > b.cols.size(); });
+    for (const Seg& s : cur_segs) {
+      seg_target.push_back(s.target);
+      for (size_t k = 0; k < s.cols.size(); ++k) {
+        const int32_t piece = s.cols[k] / CTB_PIECE;
+        const int32_t lp = (int32_t)(std::lower_bound(cur_pieces.begin(), cur_pieces.end(), piece) -
+                                     cur_pieces.begin());
+        ent_loc.push_back((uint16_t)(lp * CTB_PIECE + s.cols[k] % CTB_PIECE));
+        ent_w.push_back(s.ws[k]);
+      }
+      seg_ent_ptr.push_back((int32_t)ent_w.size());
+    }
+    pieces.insert(pieces.end(), cur_pieces.begin(), cur_pieces.end());
+    b_piece_ptr.push_back((int32_t)pieces.size());
+    b_seg_ptr.push_back((int32_t)seg_target.size());
+    max_cells = std::max<int32_t>(max_cells, (int32_t)cur_pieces.size() * CTB_PIECE);
+    cur_pieces.clear();
+    cur_segs.clear();
+  }
+};
+
+template <typename T>
+int upload(T** dptr, const std::vector<T>& h) {
+  const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  CTB_CUDA(cudaMalloc((void**)dptr, bytes));
+  if (!h.empty()) CTB_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return CTB_OK;
+}
+
+}  // namespace
+
+extern "C" void ctb_plan_free(ctb_plan* p) {
+  if (!p) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(p->device);
+  cudaFree(p->d_row_cell); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_w);
+  cudaFree(p->d_den); cudaFree(p->d_b_piece_ptr); cudaFree(p->d_pieces); cudaFree(p->d_b_seg_ptr);
+  cudaFree(p->d_seg_target); cudaFree(p->d_seg_ent_ptr); cudaFree(p->d_ent_w);
+  cudaFree(p->d_ent_loc); cudaFree(p->d_split_region); cudaFree(p->d_split_slot_ptr);
+  cudaSetDevice(prev);
+  delete p;
+}
+
+static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* lat_phys,
+                           int32_t nlat_phys, const double* grid_lon, int32_t nlon,
+                           const int32_t* lon_phys, int32_t nlon_phys, const double* row_lat,
+                           const double* row_lon, const int32_t* region_code,
+                           const double* w_primary, const double* w_backup, int64_t n_rows,
+                           int32_t R, const ctb_plan_opts* opts, ctb_plan* P, int64_t* bad_row,
+                           int32_t* bad_axis) {
+  const int64_t ncell = (int64_t)nlat_phys * nlon_phys;
+  if (nlat <= 0 || nlon <= 0 || n_rows < 0 || R < 0 || nlat_phys < nlat || nlon_phys < nlon ||
+      ncell >= (1ll << 31) || n_rows >= (1ll << 31)) {
+    ctb_set_error("ctb_plan_build: invalid sizes (nlat=%d nlon=%d n_rows=%lld R=%d)", nlat, nlon,
+                  (long long)n_rows, R);
+    return CTB_ERR_INVALID;
+  }
+  for (int64_t k = 0; k < n_rows; ++k)
+    if (region_code[k] < -1 || region_code[k] >= R) {
+      ctb_set_error("ctb_plan_build: region_code[%lld]=%d out of range", (long long)k,
+                    region_code[k]);
+      return CTB_ERR_INVALID;
+    }
+  P->R = R; P->n_rows = n_rows; P->ncell = ncell; P->nlat_phys = nlat_phys; P->nlon_phys = nlon_phys;
+
+  // ---- sorted label tables (host sort of <= a few thousand labels) ----
+  auto sort_labels = [](const double* lab, int n, std::vector<double>& s, std::vector<int32_t>& o) {
+    o.resize(n);
+    std::iota(o.begin(), o.end(), 0);
+    std::stable_sort(o.begin(), o.end(), [&](int a, int b) { return lab[a] < lab[b]; });
+    s.resize(n);
+    for (int i = 0; i < n; ++i) s[i] = lab[o[i]];
+  };
+  std::vector<double> slat, slon;
+  std::vector<int32_t> olat, olon;
+  sort_labels(grid_lat, nlat, slat, olat);
+  sort_labels(grid_lon, nlon, slon, olon);
+
+  // ---- device K0 ----
+  double *d_slat = nullptr, *d_slon = nullptr, *d_rlat = nullptr, *d_rlon = nullptr, *d_wp = nullptr,
+         *d_wb = nullptr, *d_row_w = nullptr;
+  int32_t *d_olat = nullptr, *d_olon = nullptr, *d_latp = nullptr, *d_lonp = nullptr;
+  uint32_t *d_keys = nullptr, *d_keys_s = nullptr;
+  int32_t *d_rows = nullptr, *d_rows_s = nullptr;
+  unsigned long long* d_bad = nullptr;
+  void* d_tmp = nullptr;
+  struct Guard {
+    std::vector<void**> v;
+    ~Guard() { for (void** p : v) cudaFree(*p); }
+  } guard;
+  guard.v = {(void**)&d_slat, (void**)&d_slon, (void**)&d_rlat, (void**)&d_rlon, (void**)&d_wp,
+             (void**)&d_wb, (void**)&d_row_w, (void**)&d_olat, (void**)&d_olon, (void**)&d_latp,
+             (void**)&d_lonp, (void**)&d_keys, (void**)&d_keys_s, (void**)&d_rows,
+             (void**)&d_rows_s, (void**)&d_bad, &d_tmp};
+
+  const size_t nr = (size_t)std::max<int64_t>(n_rows, 1);
+  CTB_CUDA(cudaMalloc(&d_slat, nlat * sizeof(double)));
+  CTB_CUDA(cudaMalloc(&d_slon, nlon * sizeof(double)));
+  CTB_CUDA(cudaMalloc(&d_olat, nlat * sizeof(int32_t)));
+  CTB_CUDA(cudaMalloc(&d_olon, nlon * sizeof(int32_t)));
+  CTB_CUDA(cudaMemcpy(d_slat, slat.data(), nlat * sizeof(double), cudaMemcpyHostToDevice));
+  CTB_CUDA(cudaMemcpy(d_slon, slon.data(), nlon * sizeof(double), cudaMemcpyHostToDevice));
+  CTB_CUDA(cudaMemcpy(d_olat, olat.data(), nlat * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CTB_CUDA(cudaMemcpy(d_olon, olon.data(), nlon * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (lat_phys) {
+    CTB_CUDA(cudaMalloc(&d_latp, nlat * sizeof(int32_t)));
+    CTB_CUDA(cudaMemcpy(d_latp, lat_phys, nlat * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  if (lon_phys) {
+    CTB_CUDA(cudaMalloc(&d_lonp, nlon * sizeof(int32_t)));
+    CTB_CUDA(cudaMemcpy(d_lonp, lon_phys, nlon * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  CTB_CUDA(cudaMalloc(&d_rlat, nr * sizeof(double)));
+  CTB_CUDA(cudaMalloc(&d_rlon, nr * sizeof(double)));
+  CTB_CUDA(cudaMalloc(&d_wp, nr * sizeof(double)));
+  CTB_CUDA(cudaMalloc(&d_wb, nr * sizeof(double)));
+  CTB_CUDA(cudaMalloc(&d_row_w, nr * sizeof(double)));
+  CTB_CUDA(cudaMalloc(&P->d_row_cell, nr * sizeof(int32_t)));
+  CTB_CUDA(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+  CTB_CUDA(cudaMemset(d_bad, 0xff, sizeof(unsigned long long)));
+  CTB_CUDA(cudaMemcpy(d_rlat, row_lat, n_rows * sizeof(double), cudaMemcpyHostToDevice));
+  CTB_CUDA(cudaMemcpy(d_rlon, row_lon, n_rows * sizeof(double), cudaMemcpyHostToDevice));
+  CTB_CUDA(cudaMemcpy(d_wp, w_primary, n_rows * sizeof(double), cudaMemcpyHostToDevice));
+  CTB_CUDA(cudaMemcpy(d_wb, w_backup, n_rows * sizeof(double), cudaMemcpyHostToDevice));
+
+  if (n_rows > 0) {
+    k0_match_kernel<<<(unsigned)((n_rows + 255) / 256), 256>>>(
+        d_slat, d_olat, nlat, d_latp, d_slon, d_olon, nlon, d_lonp, nlon_phys, d_rlat, d_rlon, d_wp,
+        d_wb, n_rows, P->d_row_cell, d_row_w, d_bad);
+    CTB_LAUNCH_CHECK();
+  }
+  unsigned long long bad = ~0ull;
+  CTB_CUDA(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+  if (bad != ~0ull) {
+    if (bad_row) *bad_row = (int64_t)(bad >> 1);
+    if (bad_axis) *bad_axis = (int32_t)(bad & 1);
+    ctb_set_error("not all values found in index '%s' (weights row %lld)", (bad & 1) ? "lon" : "lat",
+                  (long long)(bad >> 1));
+    return CTB_ERR_LABEL_NOT_FOUND;
+  }
+
+  // stable sort of rows by region code (code -1 -> 0xffffffff sorts last)
+  std::vector<uint32_t> h_keys(nr);
+  for (int64_t k = 0; k < n_rows; ++k) h_keys[k] = (uint32_t)region_code[k];
+  std::vector<int32_t> h_iota(nr);
+  std::iota(h_iota.begin(), h_iota.end(), 0);
+  CTB_CUDA(cudaMalloc(&d_keys, nr * sizeof(uint32_t)));
+  CTB_CUDA(cudaMalloc(&d_keys_s, nr * sizeof(uint32_t)));
+  CTB_CUDA(cudaMalloc(&d_rows, nr * sizeof(int32_t)));
+  CTB_CUDA(cudaMalloc(&d_rows_s, nr * sizeof(int32_t)));
+  CTB_CUDA(cudaMemcpy(d_keys, h_keys.data(), n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CTB_CUDA(cudaMemcpy(d_rows, h_iota.data(), n_rows * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (n_rows > 0) {
+    size_t tmp_bytes = 0;
+    CTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_rows, d_rows_s,
+                                             (int)n_rows));
+    CTB_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
+    CTB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_s, d_rows, d_rows_s,
+                                             (int)n_rows));
+    g_ctb_launches.fetch_add(1);
+  }
+  int32_t* d_rp_all = nullptr;  // row pointers over ALL rows with a valid region
+  CTB_CUDA(cudaMalloc(&d_rp_all, (R + 1) * sizeof(int32_t)));
+  guard.v.push_back((void**)&d_rp_all);
+  k0_rowptr_kernel<<<(R + 1 + 255) / 256, 256>>>(d_keys_s, n_rows, R, d_rp_all);
+  CTB_LAUNCH_CHECK();
+  CTB_CUDA(cudaMalloc(&P->d_den, std::max(R, 1) * sizeof(double)));
+  if (R > 0) {
+    k0_den_kernel<<<(R + 255) / 256, 256>>>(d_rp_all, d_rows_s, d_row_w, R, P->d_den);
+    CTB_LAUNCH_CHECK();
+  }
+
+  // ---- bring the sorted structure to the host planner ----
+  std::vector<int32_t> rp_all(R + 1), rows_s(nr);
+  P->h_row_cell.resize(n_rows);
+  P->h_row_w.resize(n_rows);
+  P->h_den.resize(R);
+  CTB_CUDA(cudaMemcpy(rp_all.data(), d_rp_all, (R + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CTB_CUDA(cudaMemcpy(rows_s.data(), d_rows_s, n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CTB_CUDA(cudaMemcpy(P->h_row_cell.data(), P->d_row_cell, n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CTB_CUDA(cudaMemcpy(P->h_row_w.data(), d_row_w, n_rows * sizeof(double), cudaMemcpyDeviceToHost));
+  CTB_CUDA(cudaMemcpy(P->h_den.data(), P->d_den, R * sizeof(double), cudaMemcpyDeviceToHost));
+
+  // kept CSR: drop rows whose weight is NaN or 0 -- they add nothing to the
+  // numerator (NaN product is skipped; 0*x is 0 or NaN) and are already in den.
+  std::vector<int32_t> row_ptr(R + 1, 0), col;
+  std::vector<double> w;
+  col.reserve(n_rows);
+  w.reserve(n_rows);
+  int32_t max_rows = 0;
+  for (int32_t r = 0; r < R; ++r) {
+    for (int32_t k = rp_all[r]; k < rp_all[r + 1]; ++k) {
+      const int32_t row = rows_s[k];
+      const double ww = P->h_row_w[row];
+      if (ww == ww && ww != 0.0) {
+        col.push_back(P->h_row_cell[row]);
+        w.push_back(ww);
+      }
+    }
+    row_ptr[r + 1] = (int32_t)col.size();
+    max_rows = std::max(max_rows, row_ptr[r + 1] - row_ptr[r]);
+  }
+  P->nnz = (int64_t)col.size();
+
+  // ---- staging bundles ----
+  int32_t bytes_cd = opts && opts->stage_bytes_per_cell_day > 0 ? opts->stage_bytes_per_cell_day : 4;
+  int32_t budget = opts && opts->smem_budget_bytes > 0 ? opts->smem_budget_bytes : 72 * 1024;
+  int32_t cap_cells = budget / (CTB_S * bytes_cd);
+  cap_cells -= cap_cells % CTB_PIECE;
+  cap_cells = std::min(cap_cells, 65536 - CTB_PIECE);
+  if (cap_cells < 2 * CTB_PIECE) {
+    ctb_set_error("ctb_plan_build: smem budget %d too small", budget);
+    return CTB_ERR_INVALID;
+  }
+  const int32_t cap_pieces = cap_cells / CTB_PIECE;
+
+  uint32_t hn = 1;
+  while ((int32_t)hn < std::max(nlat_phys, nlon_phys)) hn <<= 1;
+  std::vector<Region> regs;
+  std::vector<int32_t> empty_regions;
+  regs.reserve(R);
+  for (int32_t r = 0; r < R; ++r) {
+    if (row_ptr[r + 1] == row_ptr[r]) {
+      // no kept rows: out = 0 / den (NaN when den == 0), written by the fix-up kernel
+      // as a "split" region with an empty slot range
+      empty_regions.push_back(r);
+      continue;
+    }
+    double ci = 0, cj = 0;
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+      ci += col[k] / nlon_phys;
+      cj += col[k] % nlon_phys;
+    }
+    const int32_t n = row_ptr[r + 1] - row_ptr[r];
+    regs.push_back({r, row_ptr[r], row_ptr[r + 1],
+                    hilbert_xy2d(hn, (uint32_t)(cj / n), (uint32_t)(ci / n))});
+  }
+  std::stable_sort(regs.begin(), regs.end(),
+                   [](const Region& a, const Region& b) { return a.hkey < b.hkey; });
+
+  const int64_t npiece_grid = (ncell + CTB_PIECE - 1) / CTB_PIECE;
+  std::vector<int32_t> stamp(npiece_grid, -1);   // piece -> bundle generation that holds it
+  std::vector<uint8_t> seen(npiece_grid, 0);     // piece referenced at all
+  std::vector<uint8_t> cell_seen(ncell, 0);
+  int32_t gen = 0;
+  BundleBuilder B;
+  std::vector<int32_t> split_region, split_slot_ptr{0};
+  int32_t n_scratch = 0;
+  std::vector<int32_t> newp;
+
+  auto add_segment = [&](int32_t target, const int32_t* cols, const double* ws, int32_t n) {
+    BundleBuilder::Seg s;
+    s.target = target;
+    s.cols.assign(cols, cols + n);
+    s.ws.assign(ws, ws + n);
+    for (int32_t k = 0; k < n; ++k) {
+      const int32_t p = cols[k] / CTB_PIECE;
+      if (stamp[p] != gen) { stamp[p] = gen; B.cur_pieces.push_back(p); }
+    }
+    B.cur_segs.push_back(std::move(s));
+  };
+
+  for (const Region& g : regs) {
+    const int32_t n = g.e1 - g.e0;
+    // distinct new pieces this region would add to the open bundle
+    newp.clear();
+    for (int32_t k = g.e0; k < g.e1; ++k) {
+      const int32_t p = col[k] / CTB_PIECE;
+      if (stamp[p] != gen) newp.push_back(p);
+    }
+    std::sort(newp.begin(), newp.end());
+    newp.erase(std::unique(newp.begin(), newp.end()), newp.end());
+    if ((int32_t)(B.cur_pieces.size() + newp.size()) <= cap_pieces) {
+      add_segment(g.r, &col[g.e0], &w[g.e0], n);
+      continue;
+    }
+    // does it fit an empty bundle?
+    std::vector<int32_t> own;
+    own.reserve(n);
+    for (int32_t k = g.e0; k < g.e1; ++k) own.push_back(col[k] / CTB_PIECE);
+    std::sort(own.begin(), own.end());
+    own.erase(std::unique(own.begin(), own.end()), own.end());
+    B.close();
+    ++gen;
+    if ((int32_t)own.size() <= cap_pieces) {
+      add_segment(g.r, &col[g.e0], &w[g.e0], n);
+      continue;
+    }
+    // split: order the region's rows by cell, cut into fragments of <= cap pieces
+    std::vector<int32_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(),
+                     [&](int a, int b) { return col[g.e0 + a] < col[g.e0 + b]; });
+    std::vector<int32_t> fc;
+    std::vector<double> fw;
+    int32_t fpieces = 0, last_piece = -1;
+    split_region.push_back(g.r);
+    auto flush = [&]() {
+      if (fc.empty()) return;
+      add_segment(~n_scratch, fc.data(), fw.data(), (int32_t)fc.size());
+      ++n_scratch;
+      B.close();
+      ++gen;
+      fc.clear(); fw.clear(); fpieces = 0; last_piece = -1;
+    };
+    for (int32_t q = 0; q < n; ++q) {
+      const int32_t c = col[g.e0 + idx[q]];
+      const int32_t p = c / CTB_PIECE;
+      if (p != last_piece) {
+        if (fpieces == cap_pieces) flush();
+        ++fpieces;
+        last_piece = p;
+      }
+      fc.push_back(c);
+      fw.push_back(w[g.e0 + idx[q]]);
+    }
+    flush();
+    split_slot_ptr.push_back(n_scratch);
+  }
+  B.close();
+  for (int32_t r : empty_regions) {
+    split_region.push_back(r);
+    split_slot_ptr.push_back(n_scratch);
+  }
+
+  int64_t U = 0, pieces_distinct = 0;
+  for (int64_t k = 0; k < P->nnz; ++k) {
+    if (!cell_seen[col[k]]) { cell_seen[col[k]] = 1; ++U; }
+    if (!seen[col[k] / CTB_PIECE]) { seen[col[k] / CTB_PIECE] = 1; ++pieces_distinct; }
+  }
+
+  // ---- upload ----
+  int rc;
+  if ((rc = upload(&P->d_row_ptr, row_ptr))) return rc;
+  if ((rc = upload(&P->d_col, col))) return rc;
+  if ((rc = upload(&P->d_w, w))) return rc;
+  if ((rc = upload(&P->d_b_piece_ptr, B.b_piece_ptr))) return rc;
+  if ((rc = upload(&P->d_pieces, B.pieces))) return rc;
+  if ((rc = upload(&P->d_b_seg_ptr, B.b_seg_ptr))) return rc;
+  if ((rc = upload(&P->d_seg_target, B.seg_target))) return rc;
+  if ((rc = upload(&P->d_seg_ent_ptr, B.seg_ent_ptr))) return rc;
+  if ((rc = upload(&P->d_ent_w, B.ent_w))) return rc;
+  if ((rc = upload(&P->d_ent_loc, B.ent_loc))) return rc;
+  if ((rc = upload(&P->d_split_region, split_region))) return rc;
+  if ((rc = upload(&P->d_split_slot_ptr, split_slot_ptr))) return rc;
+  P->n_bundles = (int32_t)B.b_piece_ptr.size() - 1;
+  P->n_segments = (int32_t)B.seg_target.size();
+  P->n_split = (int32_t)split_region.size();
+  P->n_scratch = n_scratch;
+
+  ctb_plan_info& I = P->info;
+  I.n_rows = n_rows; I.nnz = P->nnz; I.n_cells_distinct = U; I.n_cells_grid = ncell;
+  I.n_regions = R; I.n_bundles = P->n_bundles; I.n_pieces = (int64_t)B.pieces.size();
+  I.n_pieces_distinct = pieces_distinct; I.n_split_regions = P->n_split;
+  I.n_scratch_slots = n_scratch; I.cap_cells = cap_cells; I.max_bundle_cells = B.max_cells;
+  I.time_block = CTB_TB; I.max_region_rows = max_rows;
+  CTB_CUDA(cudaDeviceSynchronize());
+  return CTB_OK;
+}
+
+extern "C" int ctb_plan_build(const double* grid_lat, int32_t nlat, const int32_t* lat_phys,
+                              int32_t nlat_phys, const double* grid_lon, int32_t nlon,
+                              const int32_t* lon_phys, int32_t nlon_phys, const double* row_lat,
+                              const double* row_lon, const int32_t* region_code,
+                              const double* w_primary, const double* w_backup, int64_t n_rows,
+                              int32_t n_regions, const ctb_plan_opts* opts, int device,
+                              ctb_plan** out, int64_t* bad_row, int32_t* bad_axis) {
+  if (!out || !grid_lat || !grid_lon || (n_rows > 0 && (!row_lat || !row_lon || !region_code ||
+                                                        !w_primary || !w_backup))) {
+    ctb_set_error("ctb_plan_build: null argument");
+    return CTB_ERR_INVALID;
+  }
+  *out = nullptr;
+  int prev = 0;
+  CTB_CUDA(cudaGetDevice(&prev));
+  CTB_CUDA(cudaSetDevice(device));
+  ctb_plan* P = new ctb_plan();
+  P->device = device;
+  const int rc = plan_build_impl(grid_lat, nlat, lat_phys, nlat_phys, grid_lon, nlon, lon_phys,
+                                 nlon_phys, row_lat, row_lon, region_code, w_primary, w_backup,
+                                 n_rows, n_regions, opts, P, bad_row, bad_axis);
+  cudaSetDevice(prev);
+  if (rc != CTB_OK) {
+    ctb_plan_free(P);
+    return rc;
+  }
+  *out = P;
+  return CTB_OK;
+}
+
+extern "C" int ctb_plan_get_info(const ctb_plan* plan, ctb_plan_info* info) {
+  if (!plan || !info) { ctb_set_error("null argument"); return CTB_ERR_INVALID; }
+  *info = plan->info;
+  return CTB_OK;
+}
+
+extern "C" int ctb_plan_row_cells(const ctb_plan* plan, int32_t* out) {
+  if (!plan || !out) { ctb_set_error("null argument"); return CTB_ERR_INVALID; }
+  std::memcpy(out, plan->h_row_cell.data(), plan->h_row_cell.size() * sizeof(int32_t));
+  return CTB_OK;
+}
+
+extern "C" int ctb_plan_den(const ctb_plan* plan, double* out) {
+  if (!plan || !out) { ctb_set_error("null argument"); return CTB_ERR_INVALID; }
+  std::memcpy(out, plan->h_den.data(), plan->h_den.size() * sizeof(double));
+  return CTB_OK;
+}
+
+extern "C" int ctb_plan_row_weights(const ctb_plan* plan, double* out) {
+  if (!plan || !out) { ctb_set_error("null argument"); return CTB_ERR_INVALID; }
+  std::memcpy(out, plan->h_row_w.data(), plan->h_row_w.size() * sizeof(double));
+  return CTB_OK;
+}

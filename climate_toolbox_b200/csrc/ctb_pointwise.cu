@@ -1,0 +1,108 @@
+// Pointwise helpers: materialise what the reference materialises when a caller
+// asks for it (`.values` of a transformed or reindexed variable).  Not on the
+// fused hot path, which never materialises these intermediates.
+//   ctb_transform   : transformations.py:69-89 (Snyder EDD), :139-141 (GDD), :189 (poly)
+//   ctb_gather_rows : aggregations.py:27 (ds.sel pointwise gather)
+#include <algorithm>
+
+#include "ctb_internal.cuh"
+
+namespace {
+
+template <typename TIN, int KIND, int NOUT>
+__global__ void transform_kernel(const TIN* __restrict__ x0, const TIN* __restrict__ x1, int64_t n,
+                                 CtbTr tr, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double a = (double)x0[i];
+    double b = 0.0;
+    if constexpr (KIND == CTB_TR_EDD || KIND == CTB_TR_GDD) b = (double)x1[i];
+    double f[NOUT];
+    ctb_apply<KIND, NOUT>(tr, a, b, f);
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) out[(size_t)j * n + i] = f[j];
+  }
+}
+
+template <typename TIN, int KIND, int NOUT>
+int launch_tr(const void* x0, const void* x1, int64_t n, const CtbTr& tr, double* out, cudaStream_t st) {
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 32);
+  transform_kernel<TIN, KIND, NOUT><<<grid, 256, 0, st>>>((const TIN*)x0, (const TIN*)x1, n, tr, out);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+template <typename TIN, int KIND>
+int tr_nout(const void* x0, const void* x1, int64_t n, const CtbTr& tr, int n_out, double* out, cudaStream_t st) {
+  switch (n_out) {
+    case 1: return launch_tr<TIN, KIND, 1>(x0, x1, n, tr, out, st);
+    case 2: return launch_tr<TIN, KIND, 2>(x0, x1, n, tr, out, st);
+    case 3: return launch_tr<TIN, KIND, 3>(x0, x1, n, tr, out, st);
+    case 4: return launch_tr<TIN, KIND, 4>(x0, x1, n, tr, out, st);
+  }
+  return CTB_ERR_INVALID;
+}
+
+template <typename TIN>
+int tr_kind(const void* x0, const void* x1, int64_t n, const CtbTr& tr, int kind, int n_out, double* out,
+            cudaStream_t st) {
+  switch (kind) {
+    case CTB_TR_IDENTITY: return launch_tr<TIN, CTB_TR_IDENTITY, 1>(x0, x1, n, tr, out, st);
+    case CTB_TR_POLY: return tr_nout<TIN, CTB_TR_POLY>(x0, x1, n, tr, n_out, out, st);
+    case CTB_TR_EDD: return tr_nout<TIN, CTB_TR_EDD>(x0, x1, n, tr, n_out, out, st);
+    case CTB_TR_GDD: return tr_nout<TIN, CTB_TR_GDD>(x0, x1, n, tr, n_out, out, st);
+  }
+  return CTB_ERR_INVALID;
+}
+
+template <typename TIN, int LAYOUT>
+__global__ void gather_rows_kernel(const TIN* __restrict__ x, int64_t stride,
+                                   const int32_t* __restrict__ row_cell, int64_t n_rows,
+                                   const int32_t* __restrict__ tix, int64_t T, TIN* __restrict__ out) {
+  const int64_t total = n_rows * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k, t;
+    if (LAYOUT == CTB_LAYOUT_TIME_MAJOR) { t = i / n_rows; k = i % n_rows; }
+    else { k = i / T; t = i % T; }
+    const int64_t tp = tix ? tix[t] : t;
+    const int64_t c = row_cell[k];
+    out[i] = (LAYOUT == CTB_LAYOUT_TIME_MAJOR) ? x[tp * stride + c] : x[c * stride + tp];
+  }
+}
+
+}  // namespace
+
+extern "C" int ctb_transform(const void* x0, const void* x1, int dtype, int64_t n, int transform,
+                             const double* params, int n_params, int n_out, double* out, void* stream) {
+  if (!x0 || (!out && n > 0) || n < 0) { ctb_set_error("ctb_transform: bad argument"); return CTB_ERR_INVALID; }
+  if (dtype != CTB_F32 && dtype != CTB_F64) { ctb_set_error("dtype=%d unsupported", dtype); return CTB_ERR_INVALID; }
+  CtbTr tr;
+  int rc = ctb_pack_transform(transform, params, n_params, n_out, &tr);
+  if (rc) return rc;
+  if (ctb_tr_nin(transform) == 2 && !x1) { ctb_set_error("transform needs two inputs"); return CTB_ERR_INVALID; }
+  if (n == 0) return CTB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == CTB_F32 ? tr_kind<float>(x0, x1, n, tr, transform, n_out, out, st)
+                          : tr_kind<double>(x0, x1, n, tr, transform, n_out, out, st);
+}
+
+extern "C" int ctb_gather_rows(const ctb_plan* P, const void* x, int dtype, int layout, int64_t stride,
+                               const int32_t* time_index, int64_t T, void* out, void* stream) {
+  if (!P || !x || (!out && T > 0 && P->n_rows > 0) || T < 0) { ctb_set_error("ctb_gather_rows: bad argument"); return CTB_ERR_INVALID; }
+  if (dtype != CTB_F32 && dtype != CTB_F64) { ctb_set_error("dtype=%d unsupported", dtype); return CTB_ERR_INVALID; }
+  const int64_t total = P->n_rows * T;
+  if (total == 0) return CTB_OK;
+  int prev = 0;
+  CTB_CUDA(cudaGetDevice(&prev));
+  if (prev != P->device) CTB_CUDA(cudaSetDevice(P->device));
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CTB_G(TIN, L) gather_rows_kernel<TIN, L><<<grid, 256, 0, st>>>((const TIN*)x, stride, P->d_row_cell, P->n_rows, time_index, T, (TIN*)out)
+  if (dtype == CTB_F32) { if (layout == CTB_LAYOUT_TIME_MAJOR) CTB_G(float, CTB_LAYOUT_TIME_MAJOR); else CTB_G(float, CTB_LAYOUT_CELL_MAJOR); }
+  else { if (layout == CTB_LAYOUT_TIME_MAJOR) CTB_G(double, CTB_LAYOUT_TIME_MAJOR); else CTB_G(double, CTB_LAYOUT_CELL_MAJOR); }
+#undef CTB_G
+  CTB_LAUNCH_CHECK();
+  if (prev != P->device) cudaSetDevice(prev);
+  return CTB_OK;
+}

@@ -1,0 +1,166 @@
+/* ctb.h -- C-ABI of libctb.so: B200 (sm_100a) grid->region aggregation.
+ *
+ * The reference (ClimateImpactLab/climate_toolbox) has NO FFI layer for this
+ * path: it is a plain Python function API over xarray
+ * (climate_toolbox/aggregations/aggregations.py:87-124).  This header is the
+ * boundary a maintainer would bind (ctypes) to replace the
+ * bodies of:
+ *
+ *   _reindex_spatial_data_to_regions      aggregations.py:8-32   -> ctb_plan_build, ctb_gather_rows
+ *   _aggregate_reindexed_data_to_regions  aggregations.py:35-84  -> ctb_plan_build (weights, den), ctb_aggregate
+ *   tas_poly arithmetic                   transformations.py:189 -> ctb_aggregate(transform=POLY) / ctb_transform
+ *   snyder_edd / snyder_gdd arithmetic    transformations.py:69-89, 139-141
+ *                                                                 -> ctb_aggregate(transform=EDD|GDD) / ctb_transform
+ *   convert_lons_split data shuffle       utils/utils.py:33-40   -> lon_phys[] of ctb_plan_build (index remap, no copy)
+ *   remove_leap_days data copy            utils/utils.py:77-80   -> time_index[] of ctb_aggregate
+ *
+ * Conventions: plain pointers + sizes, no C++/torch types.  "host" pointers are
+ * read on the CPU during the call; "device" pointers must be CUDA device memory
+ * on the plan's device and are only touched by stream-ordered work on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).  Every entry
+ * point returns CTB_OK (0) or a CTB_ERR_* code; ctb_last_error() gives the
+ * thread-local message.  A plan is immutable after build and may be shared
+ * across threads and streams.  There is no CPU fallback anywhere: without a
+ * CUDA device every compute entry point fails with CTB_ERR_CUDA.
+ */
+#ifndef CTB_H_
+#define CTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTB_VERSION 100
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  CTB_OK = 0,
+  CTB_ERR_LABEL_NOT_FOUND = 1, /* a weights row's lat/lon label is not in the grid
+                                  (exact float64 equality; xarray .sel KeyError,
+                                  aggregations.py:27).  *bad_row = first such row */
+  CTB_ERR_CUDA = 2,
+  CTB_ERR_INVALID = 3,
+  CTB_ERR_UNSUPPORTED = 4
+};
+
+/* ---- enums --------------------------------------------------------------- */
+enum { CTB_F32 = 0, CTB_F64 = 1 };
+
+/* memory layout of the gridded input seen as 2-D (time, flat cell):
+ *   TIME_MAJOR: x[t * plane_stride + cell]   BCSD netCDF (time, lat, lon)
+ *   CELL_MAJOR: x[cell * cell_stride + t]    reference test fixture (lat, lon, time) */
+enum { CTB_LAYOUT_TIME_MAJOR = 0, CTB_LAYOUT_CELL_MAJOR = 1 };
+
+/* gridcell-level transforms fused into the gather (params are host doubles):
+ *   IDENTITY  n_in=1            f = x
+ *   POLY      n_in=1  params = {offset, p_1..p_nout}   f_j = (x - offset)^p_j   transformations.py:189
+ *   EDD       n_in=2  params = {e_1..e_nout}           f_j = SnyderEDD(tmin=x0,tmax=x1,e_j)  transformations.py:69-89
+ *   GDD       n_in=2  params = {lo_1,hi_1,..}          f_j = EDD(lo_j) - EDD(hi_j)           transformations.py:139-141 */
+enum { CTB_TR_IDENTITY = 0, CTB_TR_POLY = 1, CTB_TR_EDD = 2, CTB_TR_GDD = 3 };
+#define CTB_MAX_OUT 4
+
+typedef struct ctb_plan ctb_plan;
+
+/* Planner knobs (all optional; zero = default). */
+typedef struct ctb_plan_opts {
+  int32_t stage_bytes_per_cell_day; /* bytes one gridcell-day occupies in the staging
+                                       tile: n_in * sizeof(elem); default 4 (one f32) */
+  int32_t smem_budget_bytes;        /* staging shared memory per CTA; default 72 KiB
+                                       (three CTAs per SM) */
+  int32_t reserved[6];
+} ctb_plan_opts;
+
+typedef struct ctb_plan_info {
+  int64_t n_rows;          /* rows of the weights table */
+  int64_t nnz;             /* rows kept in the CSR (finite, non-zero weight, valid region) */
+  int64_t n_cells_distinct;/* U: distinct referenced gridcells (of kept rows) */
+  int64_t n_cells_grid;    /* nlat_phys * nlon_phys */
+  int32_t n_regions;       /* R */
+  int32_t n_bundles;       /* staging work units (x time blocks = CTAs) */
+  int64_t n_pieces;        /* 4-cell pieces staged per time step, summed over bundles */
+  int64_t n_pieces_distinct;/* distinct pieces (DRAM-side footprint per time step) */
+  int32_t n_split_regions; /* regions larger than one bundle (two-phase reduce) */
+  int32_t n_scratch_slots; /* partial-sum rows those regions need */
+  int32_t cap_cells;       /* staging capacity per bundle in cells */
+  int32_t max_bundle_cells;
+  int32_t time_block;      /* days per staging tile */
+  int32_t max_region_rows; /* largest region, in kept rows */
+} ctb_plan_info;
+
+/* ---- misc ---------------------------------------------------------------- */
+int ctb_version(void);
+const char* ctb_last_error(void);
+/* number of kernel launches issued by this library since load (for gpu_launches). */
+int64_t ctb_launch_count(void);
+
+/* ---- K0: one-time plan (region-sorted CSR + staging bundles) on device --- *
+ * Replaces aggregations.py:24-27 (label -> index, exact match) and :64-73
+ * (per-row fallback weight, region grouping).  All pointer args are HOST.
+ *
+ *  grid_lat[nlat], grid_lon[nlon] : the dataset's coordinate labels (logical order)
+ *  lat_phys[nlat], lon_phys[nlon] : physical position of each label along the
+ *        stored axis (NULL = identity).  A lazily standardised 0..360 grid
+ *        (utils.py:33-40) passes the sorted -180..180 labels in grid_lon and
+ *        the roll permutation in lon_phys.
+ *  nlat_phys, nlon_phys           : stored grid extents (cell = i*nlon_phys + j)
+ *  row_lat/row_lon[n_rows]        : weights["lat"], weights["lon"]
+ *  region_code[n_rows]            : 0..n_regions-1 = rank of weights[agglev] among its
+ *        sorted unique values (pd.factorize(sort=True)); -1 = NaN label (dropped)
+ *  w_primary/w_backup[n_rows]     : weights[aggwt], weights[backup_aggwt];
+ *        w = w_primary > 0 ? w_primary : w_backup            (aggregations.py:73)
+ *  bad_row (nullable)             : first row without a match on CTB_ERR_LABEL_NOT_FOUND,
+ *        bad_axis: 0 = lat, 1 = lon
+ */
+int ctb_plan_build(const double* grid_lat, int32_t nlat, const int32_t* lat_phys, int32_t nlat_phys,
+                   const double* grid_lon, int32_t nlon, const int32_t* lon_phys, int32_t nlon_phys,
+                   const double* row_lat, const double* row_lon, const int32_t* region_code,
+                   const double* w_primary, const double* w_backup, int64_t n_rows,
+                   int32_t n_regions, const ctb_plan_opts* opts, int device, ctb_plan** out,
+                   int64_t* bad_row, int32_t* bad_axis);
+void ctb_plan_free(ctb_plan* plan);
+int ctb_plan_get_info(const ctb_plan* plan, ctb_plan_info* info);
+/* HOST outputs: physical flat cell of every weights row (bit-exact index map), and
+ * den[r] = sum of nan->0(w) per region (aggregations.py:79). */
+int ctb_plan_row_cells(const ctb_plan* plan, int32_t* cells_out /*[n_rows]*/);
+int ctb_plan_den(const ctb_plan* plan, double* den_out /*[n_regions]*/);
+int ctb_plan_row_weights(const ctb_plan* plan, double* w_out /*[n_rows]*/);
+
+/* ---- K1+K2(+K3): fused stage + gather + segmented weighted sum ----------- *
+ * Replaces aggregations.py:75-82 (and the gather of :27) with the transform of
+ * transformations.py fused at gridcell level.
+ *
+ *  x0, x1        : DEVICE inputs (x1 only for n_in = 2), dtype CTB_F32 / CTB_F64
+ *  layout        : CTB_LAYOUT_*; stride = plane_stride (TIME_MAJOR) or cell_stride
+ *                  (CELL_MAJOR), in elements
+ *  time_index    : DEVICE int32[T] physical time step of output step t, or NULL
+ *                  for identity (leap-day removal, utils.py:77-80)
+ *  out, out_ld   : DEVICE double [n_out][R][out_ld], time contiguous, out_ld >= T
+ *                  (0 = T): out[(j*R + r)*out_ld + t] = sum_k nan->0(w_k * f_j(x[cell_k])) / den[r].
+ *                  A time-chunked caller passes out + t0 with out_ld = total T.
+ *  workspace     : DEVICE scratch of ctb_aggregate_workspace_bytes() bytes (may be
+ *                  NULL when that is 0)
+ *  variant       : 0 = auto; 1 = staged (TIME_MAJOR only); 2 = direct warp-per-region
+ */
+size_t ctb_aggregate_workspace_bytes(const ctb_plan* plan, int64_t T, int n_out);
+int ctb_aggregate(const ctb_plan* plan, const void* x0, const void* x1, int dtype, int layout,
+                  int64_t stride, const int32_t* time_index, int64_t T, int transform,
+                  const double* params, int n_params, int n_out, double* out, int64_t out_ld,
+                  void* workspace, size_t workspace_bytes, int variant, void* stream);
+
+/* ---- pointwise helpers (materialising what the reference materialises) --- */
+/* out[j][i] = f_j(x0[i], x1[i]) for i < n; DEVICE pointers (transformations.py:69-89,189). */
+int ctb_transform(const void* x0, const void* x1, int dtype, int64_t n, int transform,
+                  const double* params, int n_params, int n_out, double* out, void* stream);
+/* The (time, reshape_index) / (reshape_index, time) gather of aggregations.py:27:
+ * TIME_MAJOR: out[t*n_rows + k] = x[time_index[t]*stride + cell_k]
+ * CELL_MAJOR: out[k*T + t]      = x[cell_k*stride + time_index[t]]   (out dtype = in dtype) */
+int ctb_gather_rows(const ctb_plan* plan, const void* x, int dtype, int layout, int64_t stride,
+                    const int32_t* time_index, int64_t T, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTB_H_ */

@@ -1,0 +1,422 @@
+"""Parity of the CUDA path (through the public API and the C-ABI) against the oracle.
+
+Tolerances: index mapping bit-exact; aggregates |got-ref| <= 1e-9 * max(|ref|, S) where
+S = sum(w|f(x)|)/sum(w) is the cancellation-aware scale of SURVEY.md 7.3-6 (odd powers of
+degC and EDD near 0 cancel to ~0, where a pure relative error is undefined)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+from climate_toolbox_b200 import DataArray, Dataset, synthetic
+from climate_toolbox_b200 import _engine as E
+from climate_toolbox_b200 import _native as N
+from climate_toolbox_b200.aggregations.aggregations import (
+    _aggregate_reindexed_data_to_regions, _reindex_spatial_data_to_regions,
+    weighted_aggregate_grid_to_regions)
+from climate_toolbox_b200.io import load_bcsd
+from climate_toolbox_b200.transformations.transformations import snyder_edd, snyder_gdd, tas_poly
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_fixture.npz")
+
+
+def check(got, ref, scale=None, tol=TOL):
+    err = rel_err(got, ref, scale)
+    assert err <= tol, err
+    return err
+
+
+def oracle_agg(x, dims, lat, lon, df, aggwt, agglev, backup="areawt"):
+    ref, rd, labels = oracle.weighted_aggregate_grid_to_regions(x, dims, lat, lon, df, aggwt, agglev, backup)
+    scale = oracle.weighted_aggregate_grid_to_regions(np.abs(x), dims, lat, lon, df, aggwt, agglev, backup)[0]
+    return ref, rd, labels, scale
+
+
+@pytest.fixture
+def clim_data(ref_fix):
+    lat, lon, time, temp, _ = ref_fix
+    return Dataset({"temperature": (["lat", "lon", "time"], temp)},
+                   coords={"lon": lon, "lat": lat, "time": time})
+
+
+# ----------------------------------------------------------------------------
+# transcriptions of the reference's hot-path tests (tests/test_climate_toolbox.py:109-135)
+# ----------------------------------------------------------------------------
+def test_reindex_spatial_weights(clim_data, ref_fix):
+    weights = ref_fix[4]
+    assert not clim_data.temperature.isnull().any()
+    ds = _reindex_spatial_data_to_regions(clim_data, weights)
+    assert ds.temperature.shape == (len(ds["lon"]), len(ds["time"]))
+    assert "reshape_index" in ds.dims
+    G = np.load(GOLD, allow_pickle=True)
+    np.testing.assert_array_equal(ds.temperature.values, G["reindexed"])  # gather is bit-exact
+
+
+def test_weighting(clim_data, ref_fix):
+    weights = ref_fix[4]
+    assert np.isnan(weights["popwt"].values).any()
+    ds = _reindex_spatial_data_to_regions(clim_data, weights)
+    assert not ds.temperature.isnull().any()
+    G = np.load(GOLD, allow_pickle=True)
+
+    wtd = _aggregate_reindexed_data_to_regions(ds, "temperature", "popwt", "ISO", weights)
+    assert not wtd.temperature.isnull().any()
+    assert wtd.temperature.dims == ("ISO", "time")
+    check(wtd.temperature.values, G["agg_popwt_ISO"])
+
+    # the reference re-uses the same reindexed ds with another weight
+    wtd = _aggregate_reindexed_data_to_regions(ds, "temperature", "areawt", "ISO", weights)
+    assert not wtd.temperature.isnull().any()
+    check(wtd.temperature.values, G["agg_areawt_ISO"])
+
+
+def test_weighting_on_materialised_reindexed_data(clim_data, ref_fix):
+    """A caller that built the (reshape_index, time) array itself."""
+    weights = ref_fix[4]
+    G = np.load(GOLD, allow_pickle=True)
+    for dims, arr in ((("reshape_index", "time"), G["reindexed"]),
+                      (("time", "reshape_index"), np.ascontiguousarray(G["reindexed"].T))):
+        ds = Dataset({"temperature": (dims, arr)}, coords={"time": ref_fix[2]})
+        wtd = _aggregate_reindexed_data_to_regions(ds, "temperature", "popwt", "hierid", weights)
+        exp = G["agg_popwt_hierid"]
+        assert wtd.temperature.dims == tuple("hierid" if d == "reshape_index" else d for d in dims)
+        check(wtd.temperature.values, exp if dims[0] == "reshape_index" else exp.T)
+
+
+@pytest.mark.parametrize("aggwt", ["popwt", "areawt"])
+@pytest.mark.parametrize("agglev", ["ISO", "hierid"])
+@pytest.mark.parametrize("layout", ["lat_lon_time", "time_lat_lon"])
+def test_weighted_aggregate_on_reference_fixture(ref_fix, aggwt, agglev, layout):
+    lat, lon, time, temp, weights = ref_fix
+    G = np.load(GOLD, allow_pickle=True)
+    if layout == "lat_lon_time":
+        ds = Dataset({"temperature": (["lat", "lon", "time"], temp)},
+                     coords={"lon": lon, "lat": lat, "time": time})
+        exp, dims = G["agg_{}_{}".format(aggwt, agglev)], (agglev, "time")
+    else:
+        ds = Dataset({"temperature": (["time", "lat", "lon"], np.ascontiguousarray(temp.transpose(2, 0, 1)))},
+                     coords={"lon": lon, "lat": lat, "time": time})
+        exp, dims = G["agg_{}_{}".format(aggwt, agglev)].T, ("time", agglev)
+    out = weighted_aggregate_grid_to_regions(ds, "temperature", aggwt, agglev, weights=weights)
+    assert out.temperature.dims == dims
+    np.testing.assert_array_equal(out.coords[agglev].values, G["labels_" + agglev])
+    np.testing.assert_array_equal(out.coords["time"].values, time.values)
+    assert out.temperature.values.dtype == np.float64
+    check(out.temperature.values, exp)
+    # the caller's dataset is not mutated (the reference adds agglev/aggwt to it)
+    assert agglev not in ds.coords and aggwt not in ds.data_vars
+
+
+def test_index_map_bit_exact_with_lon_roll_and_takes(ref_fix):
+    """K0: row -> physical gridcell, exact float64 label match, lon roll folded in."""
+    d = 1.0
+    lat, lon360 = synthetic.grid_labels(d, lon_0_360=True)
+    df = synthetic.weights_table(d, 500, seed=3)
+    lon_std, perm = oracle.convert_lons_split(lon360)
+    i = oracle.exact_label_index(lat, df["lat"].values)
+    j = oracle.exact_label_index(lon_std, df["lon"].values)
+    expect = (i * len(lon360) + perm[j]).astype(np.int32)
+    grid = E.GridSpec(lat, lon_std, None, perm, len(lat), len(lon360))
+    plan = E.get_plan(grid, df, "popwt", "hierid", cache=False)
+    np.testing.assert_array_equal(plan.row_cells(), expect)
+    w = plan.row_weights()
+    np.testing.assert_array_equal(w, oracle.effective_weights(df, "popwt"))  # bit-exact incl. NaN
+    codes, labels = pd.factorize(df["hierid"].values, sort=True)
+    wz = np.nan_to_num(w, nan=0.0)
+    den = np.array([wz[codes == r].sum() for r in range(len(labels))])
+    np.testing.assert_allclose(plan.den(), den, rtol=1e-14)
+    info = plan.info
+    assert info["n_regions"] == len(labels) and info["n_rows"] == len(df)
+    kept = ~np.isnan(w) & (w != 0)
+    assert info["nnz"] == kept.sum()
+    assert info["n_cells_distinct"] == len(np.unique(expect[kept]))
+    plan.close()
+
+
+def test_label_miss_raises_keyerror(clim_data, ref_fix):
+    weights = ref_fix[4].copy()
+    weights.loc[7, "lat"] = weights.loc[7, "lat"] + 1e-10
+    with pytest.raises(KeyError, match="lat"):
+        weighted_aggregate_grid_to_regions(clim_data, "temperature", "popwt", "ISO", weights=weights)
+    with pytest.raises(KeyError):
+        weighted_aggregate_grid_to_regions(clim_data, "nope", "popwt", "ISO", weights=ref_fix[4])
+    with pytest.raises(KeyError):
+        weighted_aggregate_grid_to_regions(clim_data, "temperature", "nowt", "ISO", weights=ref_fix[4])
+
+
+# ----------------------------------------------------------------------------
+# synthetic configs at oracle-friendly sizes
+# ----------------------------------------------------------------------------
+def _config(d, R, T, seed=1234, nan_frac=0.001, lon_0_360=False, dtype=np.float32):
+    lat, lon = synthetic.grid_labels(d, lon_0_360=lon_0_360)
+    df = synthetic.weights_table(d, R, seed=seed)
+    tas, tmin, tmax = synthetic.tas_field(T, len(lat), len(lon), seed=7, nan_frac=nan_frac, dtype=dtype)
+    return lat, lon, df, tas, tmin, tmax
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("variant", [N.VARIANT_STAGED, N.VARIANT_DIRECT])
+def test_config1_shape_areawt(where, variant):
+    lat, lon, df, tas, _, _ = _config(1.0, 3000, 70)
+    data = tas if where == "host" else torch.from_numpy(tas).cuda()
+    ds = Dataset({"tas": (("time", "lat", "lon"), data)},
+                 coords={"time": pd.date_range("2001-01-01", periods=70), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "tas", "areawt", "hierid", weights=df, variant=variant)
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "areawt", "hierid")
+    assert out.tas.dims == rd and list(out.hierid.values) == list(labels)
+    check(out.tas.values, ref, scale)
+
+
+@pytest.mark.parametrize("aggwt,agglev", [("popwt", "hierid"), ("cropwt", "hierid"), ("popwt", "ISO")])
+def test_quarter_degree_sample_vs_oracle(aggwt, agglev):
+    """Full 0.25-degree grid and 24,378 regions, a few days (oracle finishes in seconds).
+    agglev=ISO makes 180 huge regions -> exercises region splitting + the fix-up kernel."""
+    lat, lon, df, tas, _, _ = _config(0.25, 24378, 5)
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": np.arange(5), "lat": lat, "lon": lon})
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, aggwt, agglev)
+    for variant in (N.VARIANT_STAGED, N.VARIANT_DIRECT):
+        out = weighted_aggregate_grid_to_regions(ds, "tas", aggwt, agglev, weights=df, variant=variant)
+        check(out.tas.values, ref, scale)
+
+
+def test_lon_0_360_and_leap_day_folded_into_the_kernel():
+    lat, lon360, df, tas, _, _ = _config(1.0, 800, 45, lon_0_360=True)
+    time = pd.date_range("2000-02-01", periods=45)
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": time, "lat": lat, "lon": lon360})
+    ds = load_bcsd(ds, "tas")                 # rename + lazy lon roll
+    out = weighted_aggregate_grid_to_regions(tas_poly(ds, 2, "tas2"), "tas2", "popwt", "hierid", weights=df)
+    lon_std, perm = oracle.convert_lons_split(lon360)
+    xt, tl = oracle.tas_poly(np.take(tas, perm, axis=2), time, 2)
+    ref, rd, labels, scale = oracle_agg(xt, ("time", "lat", "lon"), lat, lon_std, df, "popwt", "hierid")
+    assert out.tas2.shape == (44, len(labels)) and out.tas2.dims == rd
+    np.testing.assert_array_equal(out.time.values, tl)
+    check(out.tas2.values, ref, scale)
+
+
+def test_fused_tas_poly_orders_1_to_4():
+    """Config 3: four polynomial orders from one read of tas."""
+    lat, lon, df, tas, _, _ = _config(1.0, 3000, 40)
+    time = pd.date_range("2001-03-01", periods=40)
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": time, "lat": lat, "lon": lon})
+    names = ["tas", "tas-poly-2", "tas-poly-3", "tas-poly-4"]
+    ds1 = tas_poly(ds, [1, 2, 3, 4], names)
+    n0 = E.launch_count()
+    out = weighted_aggregate_grid_to_regions(ds1, names, "popwt", "hierid", weights=df)
+    assert E.launch_count() - n0 == 1          # one fused launch for all four orders
+    for p, name in zip((1, 2, 3, 4), names):
+        xt, _ = oracle.tas_poly(tas, time, p)
+        ref, rd, labels, scale = oracle_agg(xt, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+        check(out[name].values, ref, scale)
+    # a single order through the one-output instantiation agrees too
+    one = weighted_aggregate_grid_to_regions(tas_poly(ds, 3, "p3"), "p3", "popwt", "hierid", weights=df)
+    check(one.p3.values, out["tas-poly-3"].values, tol=1e-14)
+
+
+@pytest.mark.parametrize("layout", ["time_lat_lon", "lat_lon_time"])
+def test_fused_snyder_edd_gdd(layout):
+    """Config 4: EDD at two thresholds and GDD from (tasmin, tasmax), cropwt."""
+    lat, lon, df, _, tmin, tmax = _config(1.0, 3000, 33)
+    dims = ("time", "lat", "lon")
+    a, b = tmin, tmax
+    if layout == "lat_lon_time":
+        dims = ("lat", "lon", "time")
+        a, b = (np.ascontiguousarray(v.transpose(1, 2, 0)) for v in (tmin, tmax))
+    coords = {"time": np.arange(33), "lat": lat, "lon": lon}
+    tn = DataArray(torch.from_numpy(a).cuda(), dims=dims, coords=coords, attrs={"units": "K"})
+    tx = DataArray(torch.from_numpy(b).cuda(), dims=dims, coords=coords, attrs={"units": "K"})
+    ds = Dataset(coords=coords)
+    ds["edd10"] = snyder_edd(tn, tx, 283.15)
+    ds["edd30"] = snyder_edd(tn, tx, 303.15)
+    ds["gdd"] = snyder_gdd(tn, tx, 283.15, 303.15)
+    assert ds["gdd"].units == "degreedays_283.15-303.15K"
+    out = weighted_aggregate_grid_to_regions(ds, ["edd10", "edd30", "gdd"], "cropwt", "hierid", weights=df)
+    for name, f in (("edd10", oracle.snyder_edd(a, b, 283.15)), ("edd30", oracle.snyder_edd(a, b, 303.15)),
+                    ("gdd", oracle.snyder_gdd(a, b, 283.15, 303.15))):
+        ref, rd, labels, scale = oracle_agg(f, dims, lat, lon, df, "cropwt", "hierid")
+        assert out[name].dims == rd
+        check(out[name].values, ref, scale)
+
+
+def test_reference_snyder_known_answers():
+    # reference tests :231-278 through the pointwise kernel (.values)
+    tmax = DataArray(np.array([280.4963, 280.7887]), dims=("(latitude, longitude)",), attrs={"units": "K"})
+    tmin = DataArray(np.array([278.902, 278.23163]), dims=("(latitude, longitude)",), attrs={"units": "K"})
+    res = snyder_edd(tmin, tmax, threshold=273.15 + 8)
+    assert res.units == "degreedays_281.15K"
+    assert res.sum().item(0) == 0.0
+    res = snyder_gdd(tmin, tmax, threshold_low=273.15 + 1, threshold_high=273.15 + 8)
+    assert not res.units == "degreedays_281.15K"
+    assert res.units == "degreedays_274.15-281.15K"
+    assert res.sum().item(0) == pytest.approx(11, 0.1)
+    G = np.load(GOLD, allow_pickle=True)
+    check(res.values, G["gdd_274.15_281.15"], tol=1e-12)
+
+
+def test_pointwise_transform_matches_oracle():
+    _, _, _, tas, tmin, tmax = _config(2.0, 50, 6, nan_frac=0.01, dtype=np.float64)
+    dims = ("time", "lat", "lon")
+    tn = DataArray(tmin, dims=dims, attrs={"units": "K"})
+    tx = DataArray(tmax, dims=dims, attrs={"units": "K"})
+    check(snyder_edd(tn, tx, 290.0).values, oracle.snyder_edd(tmin, tmax, 290.0), tol=1e-12)
+    check(snyder_gdd(tn, tx, 285.0, 295.0).values, oracle.snyder_gdd(tmin, tmax, 285.0, 295.0),
+          scale=np.abs(oracle.snyder_edd(tmin, tmax, 285.0)), tol=1e-12)
+    t = pd.date_range("2001-01-01", periods=6)
+    ds = Dataset({"tas": (dims, tas)}, coords={"time": t})
+    check(tas_poly(ds, 4, "p4").p4.values, oracle.tas_poly(tas, t, 4)[0], tol=1e-12)
+
+
+# ----------------------------------------------------------------------------
+# edge cases
+# ----------------------------------------------------------------------------
+def _tiny(nlat=7, nlon=9, T=5, seed=0, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    lat = np.arange(nlat) * 0.5 - 1.0
+    lon = np.arange(nlon) * 0.5 + 10.0
+    x = rng.standard_normal((T, nlat, nlon)).astype(dtype) * 10
+    return lat, lon, x, rng
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("variant", [N.VARIANT_STAGED, N.VARIANT_DIRECT])
+def test_odd_grid_scalar_path_and_degenerate_regions(dtype, variant):
+    """63 cells (not a multiple of 4 -> unaligned planes, scalar staging loads); single-row
+    regions, a region whose weights are all NaN (den = 0 -> NaN), one whose data are all NaN
+    (-> 0), NaN region labels (dropped), duplicate rows, negative backup weights."""
+    lat, lon, x, rng = _tiny(dtype=dtype)
+    x[:, 2, 3] = np.nan
+    x[1, 4, 4] = np.inf
+    rows = []
+    for k in range(60):
+        rows.append((lat[rng.integers(7)], lon[rng.integers(9)], "r%02d" % rng.integers(12),
+                     rng.random(), rng.random()))
+    rows += [(lat[0], lon[0], "single", 2.0, 1.0), (lat[1], lon[1], "allnanw", np.nan, np.nan),
+             (lat[1], lon[2], "allnanw", 0.0, np.nan), (lat[2], lon[3], "allnandata", 1.0, 1.0),
+             (lat[3], lon[3], np.nan, 1.0, 1.0), (lat[5], lon[5], "dup", 1.5, 1.0),
+             (lat[5], lon[5], "dup", 1.5, 1.0), (lat[6], lon[8], "neg", -1.0, -2.0),
+             (lat[6], lon[7], "neg", 3.0, 1.0), (lat[4], lon[4], "inf", 1.0, 1.0),
+             (lat[0], lon[1], "zerow", 0.0, 0.0)]
+    df = pd.DataFrame(rows, columns=["lat", "lon", "hierid", "popwt", "areawt"])
+    ds = Dataset({"v": (("time", "lat", "lon"), x)}, coords={"time": np.arange(5), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "v", "popwt", "hierid", weights=df, variant=variant)
+    ref, rd, labels, scale = oracle_agg(x, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+    assert list(out.hierid.values) == list(labels)
+    got = out.v.values
+    li = list(labels)
+    assert np.isnan(got[:, li.index("allnanw")]).all() and np.isnan(got[:, li.index("zerow")]).all()
+    assert (got[:, li.index("allnandata")] == 0).all()
+    assert got[1, li.index("inf")] == np.inf
+    check(got, ref, scale)
+
+
+def test_empty_inputs():
+    lat, lon, x, rng = _tiny()
+    df = pd.DataFrame({"lat": [lat[0]], "lon": [lon[0]], "hierid": ["a"], "popwt": [1.0], "areawt": [1.0]})
+    ds = Dataset({"v": (("time", "lat", "lon"), x[:0])}, coords={"time": np.arange(0), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "v", "popwt", "hierid", weights=df)
+    assert out.v.shape == (0, 1)
+    ds = Dataset({"v": (("time", "lat", "lon"), x)}, coords={"time": np.arange(5), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "v", "popwt", "hierid", weights=df.iloc[:0])
+    assert out.v.shape == (5, 0)
+
+
+def test_ragged_time_and_2d_field():
+    """T not a multiple of the 32-day tile; and a (lat, lon) field without a time axis."""
+    lat, lon, df, tas, _, _ = _config(2.0, 300, 37)
+    ds = Dataset({"tas": (("time", "lat", "lon"), tas)}, coords={"time": np.arange(37), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=df)
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+    check(out.tas.values, ref, scale)
+    ds2 = Dataset({"tas": (("lat", "lon"), tas[0])}, coords={"lat": lat, "lon": lon})
+    out2 = weighted_aggregate_grid_to_regions(ds2, "tas", "popwt", "hierid", weights=df)
+    assert out2.tas.dims == ("hierid",)
+    check(out2.tas.values, ref[0], scale[0])
+
+
+def test_split_regions_small_tile():
+    """Force regions to be larger than one staging tile (tiny smem budget): the two-phase
+    partial-sum path must agree with the direct kernel and the oracle."""
+    lat, lon, df, tas, _, _ = _config(1.0, 40, 35)
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": np.arange(35), "lat": lat, "lon": lon})
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+    out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=df,
+                                             variant=N.VARIANT_STAGED, smem_budget=8 * 1024)
+    check(out.tas.values, ref, scale)
+    lat_, lon_ = synthetic.grid_labels(1.0)
+    plan = E.get_plan(E.GridSpec(lat_, lon_), df, "popwt", "hierid", smem_budget=8 * 1024)
+    assert plan.info["n_split_regions"] > 0 and plan.info["n_scratch_slots"] > plan.info["n_split_regions"]
+
+
+def test_extra_leading_dims_and_permuted_layout():
+    """(model, time, lat, lon) flattens onto the time axis; (lon, time, lat) is permuted."""
+    lat, lon, df, tas, _, _ = _config(2.0, 200, 12)
+    x4 = tas.reshape(3, 4, len(lat), len(lon))
+    ds = Dataset({"tas": (("model", "time", "lat", "lon"), x4)},
+                 coords={"model": ["a", "b", "c"], "time": np.arange(4), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "tas", "areawt", "hierid", weights=df)
+    ref, rd, labels, scale = oracle_agg(x4, ("model", "time", "lat", "lon"), lat, lon, df, "areawt", "hierid")
+    assert out.tas.dims == rd == ("model", "time", "hierid")
+    check(out.tas.values, ref, scale)
+    xp = np.ascontiguousarray(tas.transpose(2, 0, 1))
+    ds = Dataset({"tas": (("lon", "time", "lat"), xp)}, coords={"time": np.arange(12), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "tas", "areawt", "hierid", weights=df)
+    ref, rd, labels, scale = oracle_agg(xp, ("lon", "time", "lat"), lat, lon, df, "areawt", "hierid")
+    assert out.tas.dims == rd
+    check(out.tas.values, ref, scale)
+
+
+def test_prepare_spatial_weights_data_csv(tmp_path):
+    lat, lon, df, tas, _, _ = _config(2.0, 100, 3)
+    csv = df.rename(columns={"lon": "pix_cent_x", "lat": "pix_cent_y"}).reset_index(drop=True)
+    # the reference's out-of-bounds relabel: 180.125 -> -179.875 (aggregations.py:144)
+    p = tmp_path / "weights.csv"
+    csv.to_csv(p, index=False)
+    ds = Dataset({"tas": (("time", "lat", "lon"), tas)}, coords={"time": np.arange(3), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=str(p))
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon,
+                                        oracle.prepare_spatial_weights_data(str(p)), "popwt", "hierid")
+    check(out.tas.values, ref, scale)
+
+
+# ----------------------------------------------------------------------------
+# full size (BASELINE.json configs[1]): size-independent properties
+# ----------------------------------------------------------------------------
+def test_full_size_properties():
+    """0.25 deg x 24,378 regions x 365 days on the device: (a) a constant field aggregates to
+    the constant wherever den > 0; (b) linearity agg(a*x + b) = a*agg(x) + b; (c) staged and
+    direct kernels agree; (d) a 3-day slice matches the oracle."""
+    d, R, T = 0.25, 24378, 365
+    lat, lon = synthetic.grid_labels(d)
+    df = synthetic.weights_table(d, R)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = 288.0 + 10.0 * torch.randn((T, len(lat), len(lon)), generator=g, device="cuda", dtype=torch.float32)
+    coords = {"time": np.arange(T), "lat": lat, "lon": lon}
+
+    def agg(t, **kw):
+        ds = Dataset({"tas": (("time", "lat", "lon"), t)}, coords=coords)
+        return weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=df,
+                                                  keep_on_device=True, **kw)["tas"].data
+
+    y = agg(x)
+    assert y.shape == (T, R)
+    plan = E.get_plan(E.GridSpec(lat, lon), df, "popwt", "hierid")
+    ok = torch.from_numpy(plan.den() > 0).cuda()
+    c = agg(torch.full_like(x, 3.25))
+    assert torch.allclose(c[:, ok], torch.full_like(c[:, ok], 3.25), rtol=1e-12, atol=0)
+    a, b = 0.5, 16.0    # exact in fp32: a*x + b introduces fp32 rounding, so compare loosely
+    y2 = agg(x * a + b)
+    assert torch.allclose(y2[:, ok], a * y[:, ok] + b, rtol=1e-5)
+    yd = agg(x, variant=N.VARIANT_DIRECT)
+    assert torch.allclose(y[:, ok], yd[:, ok], rtol=1e-12, atol=0)
+    sl = x[100:103].cpu().numpy()
+    ref, rd, labels, scale = oracle_agg(sl, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+    check(y[100:103].cpu().numpy(), ref, scale)

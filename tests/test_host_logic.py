@@ -1,0 +1,166 @@
+"""Host-side mirror of the reference interface (named-array shim, lon standardisation,
+leap-day removal, renames): transcriptions of the reference's own utils/io tests
+(/root/reference/tests/test_climate_toolbox.py:138-228).  CPU only -- these paths
+move no data and launch no kernels."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import oracle
+from climate_toolbox_b200 import DataArray, Dataset
+from climate_toolbox_b200.io import standardize_climate_data, load_bcsd
+from climate_toolbox_b200.transformations.transformations import ordinal, tas_poly, snyder_edd
+from climate_toolbox_b200.utils.utils import (
+    convert_lons_mono, convert_lons_split, remove_leap_days,
+    rename_coords_to_lon_and_lat, rename_coords_to_longitude_and_latitude,
+    convert_kelvin_to_celsius)
+
+
+@pytest.fixture
+def clim_data(ref_fix):
+    lat, lon, time, temp, _ = ref_fix
+    return Dataset({"temperature": (["lat", "lon", "time"], temp)},
+                   coords={"lon": lon, "lat": lat, "time": time})
+
+
+def test_clim_data(clim_data):
+    assert not clim_data.temperature.isnull().any()
+    assert clim_data.temperature.shape == (90, 180, 10)
+    assert clim_data.dims["time"] == 10
+
+
+def test_rename_coords_to_lon_and_lat():
+    ds = Dataset(coords={"z": [1.20, 2.58], "long": [156.6, 38.48]})
+    ds = rename_coords_to_lon_and_lat(ds)
+    coords = ds.coords
+    assert "z" not in coords
+    assert "lon" in coords and "long" not in coords
+
+
+def test_rename_coords_to_lon_and_lat2():
+    ds = Dataset(coords={"latitude": [71.32, 72.58], "longitude": [156.6, 38.48]})
+    ds = rename_coords_to_lon_and_lat(ds)
+    coords = ds.coords
+    assert "lat" in coords and "latitude" not in coords
+    assert "lon" in coords and "longitude" not in coords
+
+
+def test_rename_coords_to_longitude_and_latitude():
+    ds = Dataset(coords={"lat": [71.32, 72.58], "lon": [156.6, 38.48]})
+    ds = rename_coords_to_longitude_and_latitude(ds)
+    coords = ds.coords
+    assert "latitude" in coords and "lat" not in coords
+    assert "longitude" in coords and "lon" not in coords
+
+
+def test_rename_coords_to_longitude_and_latitude_with_clim_data(clim_data):
+    ds = rename_coords_to_longitude_and_latitude(clim_data)
+    coords = ds.coords
+    assert "latitude" in coords and "lat" not in coords
+    assert "longitude" in coords and "lon" not in coords
+    assert ds.temperature.dims == ("latitude", "longitude", "time")
+
+
+def test_convert_lons_mono():
+    ds = Dataset(coords={"lon": [-156.6, -38.48]})
+    expected = np.array([203.4, 321.52])
+    ds = convert_lons_mono(ds, lon_name="lon")
+    np.testing.assert_array_equal(ds.lon.values, expected)
+
+
+def test_convert_lons_split():
+    ds = Dataset(coords={"longitude": [300, 320]})
+    expected = np.array([-60, -40])
+    ds = convert_lons_split(ds)
+    np.testing.assert_array_equal(ds.longitude.values, expected)
+
+
+def test_convert_lons_split_is_lazy_and_matches_oracle(clim_data):
+    ds = convert_lons_split(clim_data, lon_name="lon")
+    new, perm = oracle.convert_lons_split(clim_data.lon.values)
+    np.testing.assert_array_equal(ds.lon.values, new)
+    var = ds._vars["temperature"]
+    assert var.physical is clim_data._vars["temperature"].physical      # no data moved
+    np.testing.assert_array_equal(var.takes["lon"], perm)
+    np.testing.assert_array_equal(ds.temperature.values,
+                                  np.take(clim_data.temperature.values, perm, axis=1))
+
+
+def test_remove_leap_days():
+    da = DataArray(np.random.rand(4, 3),
+                   [("time", pd.date_range("2000-02-27", periods=4)), ("space", ["IA", "IL", "IN"])])
+    leap_day = np.datetime64("2000-02-29")
+    full = da.values
+    da = remove_leap_days(da)
+    assert leap_day not in da.coords["time"].values
+    assert da.shape == (3, 3)
+    np.testing.assert_array_equal(da.values, full[[0, 1, 3]])
+
+
+def test_remove_leap_days_with_clim_data(clim_data):
+    leap_day = np.datetime64("2000-02-29")
+    da = remove_leap_days(clim_data)
+    assert leap_day not in da.coords["time"].values
+
+
+def test_convert_kelvin_to_celsius_units(clim_data):
+    ds = convert_kelvin_to_celsius(clim_data, "temperature")
+    assert "C" in ds.data_vars["temperature"].units
+    assert ds._vars["temperature"].deferred.kind == "poly"
+
+
+def test_standardize_climate_data(clim_data):
+    ds = standardize_climate_data(clim_data)
+    coordinates = ds.coords
+    assert "lat" in coordinates and "latitude" not in coordinates
+    assert "lon" in coordinates and "longitude" not in coordinates
+    assert ds.lon.values.min() < 0 and np.all(np.diff(ds.lon.values) > 0)
+    assert load_bcsd(clim_data, "temperature").lon.values.min() < 0
+
+
+def test_sel_exact_label_keyerror(clim_data):
+    with pytest.raises(KeyError):
+        clim_data.sel(lon=np.array([0.1250001]))
+
+
+def test_ordinal():
+    assert [ordinal(n) for n in (1, 2, 3, 4, 11, 12, 13, 21, 22, 101)] == \
+        ["1st", "2nd", "3rd", "4th", "11th", "12th", "13th", "21st", "22nd", "101st"]
+
+
+def test_tas_poly_metadata():
+    t = pd.date_range("2000-02-27", periods=5)
+    ds = Dataset({"tas": (("time", "lat", "lon"), np.zeros((5, 2, 2), dtype=np.float32))},
+                 coords={"time": t, "lat": [0.0, 1.0], "lon": [0.0, 1.0]})
+    ds1 = tas_poly(ds, 3, "tas-poly-3")
+    v = ds1["tas-poly-3"]
+    assert v.shape == (4, 2, 2) and v.dims == ("time", "lat", "lon")
+    np.testing.assert_array_equal(ds1.time.values, oracle.tas_poly_time_labels(t[[0, 1, 3, 4]]))
+    assert v.attrs["units"] == "C^3" and v.attrs["variable"] == "tas-poly-3"
+    assert v.attrs["long_title"] == "Daily average temperature (degrees C) raised to the 3rd power"
+    assert tas_poly(ds, 1, "tas")["tas"].attrs["units"] == "C"
+    big = Dataset({"tas": (("time", "lat"), np.zeros((400, 1)))},
+                  coords={"time": pd.date_range("2001-01-01", periods=400), "lat": [0.0]})
+    with pytest.raises(ValueError):
+        tas_poly(big, 1, "tas")
+
+
+def test_snyder_preconditions():
+    a = DataArray(np.array([1.0, 2.0]), dims=("x",), attrs={"units": "K"})
+    b = DataArray(np.array([2.0, 1.0]), dims=("x",), attrs={"units": "K"})
+    with pytest.raises(AssertionError):
+        snyder_edd(a, b, 1.5)          # tasmax < tasmin somewhere
+    c = DataArray(np.array([2.0, 3.0]), dims=("x",), attrs={"units": "C"})
+    with pytest.raises(AssertionError):
+        snyder_edd(a, c, 1.5)          # unit mismatch
+    d = DataArray(np.array([2.0, 3.0]), dims=("x",))
+    with pytest.raises(AttributeError):
+        snyder_edd(a, d, 1.5)          # no units attr
+    r = snyder_edd(a, DataArray(np.array([2.0, 3.0]), dims=("x",), attrs={"units": "K"}), 281.15)
+    assert r.units == "degreedays_281.15K"
+
+
+def test_weights_none_is_typeerror_like_the_reference(clim_data):
+    from climate_toolbox_b200.aggregations.aggregations import weighted_aggregate_grid_to_regions
+    with pytest.raises(TypeError):
+        weighted_aggregate_grid_to_regions(clim_data, "temperature", "popwt", "ISO")
