@@ -38,7 +38,7 @@ class PlanInfo(C.Structure):
         ("n_pieces", C.c_int64), ("n_pieces_distinct", C.c_int64),
         ("n_split_regions", C.c_int32), ("n_scratch_slots", C.c_int32),
         ("cap_cells", C.c_int32), ("max_bundle_cells", C.c_int32), ("time_block", C.c_int32),
-        ("max_region_rows", C.c_int32),
+        ("max_region_rows", C.c_int32), ("max_meta_bytes", C.c_int32), ("reserved_", C.c_int32),
     ]
 
     def as_dict(self):

@@ -35,9 +35,9 @@ struct AggArgs {
   double* scratch;
   int n_scratch;
   const double* den;
-  const int32_t *b_piece_ptr, *pieces, *b_seg_ptr, *seg_target, *seg_ent_ptr;
-  const double* ent_w;
-  const uint16_t* ent_loc;
+  const int32_t *b_piece_ptr, *pieces;
+  const int64_t* b_blob_off;
+  const unsigned char* blob;
   const int32_t *row_ptr, *col;
   const double* w;
   const int32_t *split_region, *split_slot_ptr;
@@ -80,26 +80,86 @@ __device__ __forceinline__ void load_piece(const TIN* __restrict__ plane, int pi
   }
 }
 
-constexpr int STAGE_UNROLL = 4;
+// ---- mbarrier + bulk async copy (TMA 1-D; SASS: UBLKCP / SYNCS) ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <typename TIN> struct StageUnroll { static constexpr int v = sizeof(TIN) == 4 ? 8 : 4; };
+
+// one CSR entry: acc_j += w * f_j(x), NaN products skipped (skipna sum, aggregations.py:78)
+template <typename TIN, int KIND, int NOUT>
+__device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TIN r1,
+                                           double (&acc)[NOUT]) {
+  double f[NOUT];
+  ctb_apply<KIND, NOUT>(tr, (double)r0, (double)r1, f);
+  if constexpr (KIND == CTB_TR_IDENTITY || KIND == CTB_TR_POLY) {
+    // f is NaN iff x is NaN: one compare in the storage type gates all outputs
+    if (r0 == r0) {
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) acc[j] = fma(w, f[j], acc[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j)
+      if (f[j] == f[j]) acc[j] = fma(w, f[j], acc[j]);
+  }
+}
 
 template <typename TIN, int KIND, int NOUT, bool VEC>
-__global__ void __launch_bounds__(CTB_STAGE_THREADS)
+__global__ void __launch_bounds__(CTB_STAGE_THREADS, 3)
 agg_staged_kernel(const AggArgs a) {
   constexpr int NIN = NIn<KIND>::v;
   constexpr int S = CTB_S;
+  constexpr int UNR = StageUnroll<TIN>::v;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
+  __shared__ __align__(8) uint64_t s_bar;
 
   const int b = blockIdx.x;
   const int t0 = blockIdx.y * CTB_TB;
   const int p0 = a.b_piece_ptr[b];
   const int nP = a.b_piece_ptr[b + 1] - p0;
   const int nCells = nP * CTB_PIECE;
+  const int64_t blob0 = a.b_blob_off[b];
+  const uint32_t blob_bytes = (uint32_t)(a.b_blob_off[b + 1] - blob0);
   TIN* sx = reinterpret_cast<TIN*>(smem_raw);                     // [NIN][nCells][S]
   int* s_piece = reinterpret_cast<int*>(sx + (size_t)NIN * nCells * S);
+  unsigned char* s_blob = reinterpret_cast<unsigned char*>(s_piece) + ((nP * 4 + 15) & ~15);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_next = 0;
+  if (tid == 0) {
+    s_next = 0;
+    mbar_init(&s_bar, 1);
+    // segment table + weights + staged-cell indices: one bulk copy, lands during staging
+    bulk_g2s(s_blob, a.blob + blob0, blob_bytes, &s_bar);
+  }
   for (int i = tid; i < nP; i += CTB_STAGE_THREADS) s_piece[i] = a.pieces[p0 + i];
   __syncthreads();
 
@@ -114,15 +174,15 @@ agg_staged_kernel(const AggArgs a) {
       for (int in = 0; in < NIN; ++in) {
         const TIN* plane = reinterpret_cast<const TIN*>(in ? a.x1 : a.x0) + tp * a.stride;
         TIN* sd = sx + (size_t)in * nCells * S + dl;
-        for (int pg = l8; pg < nP; pg += 8 * STAGE_UNROLL) {
-          TIN v[STAGE_UNROLL][4];
+        for (int pg = l8; pg < nP; pg += 8 * UNR) {
+          TIN v[UNR][4];
 #pragma unroll
-          for (int u = 0; u < STAGE_UNROLL; ++u) {
+          for (int u = 0; u < UNR; ++u) {
             const int q = pg + 8 * u;
             if (q < nP) load_piece<TIN, VEC>(plane, s_piece[q], a.ncell, v[u]);
           }
 #pragma unroll
-          for (int u = 0; u < STAGE_UNROLL; ++u) {
+          for (int u = 0; u < UNR; ++u) {
             const int q = pg + 8 * u;
             if (q < nP) {
 #pragma unroll
@@ -134,10 +194,13 @@ agg_staged_kernel(const AggArgs a) {
     }
   }
   __syncthreads();
+  mbar_wait(&s_bar, 0);
 
   // ---------------- gather + segmented weighted sum: warp = region, lane = day --------
-  const int seg0 = a.b_seg_ptr[b];
-  const int nSeg = a.b_seg_ptr[b + 1] - seg0;
+  const CtbBlobHeader H = *reinterpret_cast<const CtbBlobHeader*>(s_blob);
+  const int4* segs = reinterpret_cast<const int4*>(s_blob + sizeof(CtbBlobHeader));
+  const double* W = reinterpret_cast<const double*>(s_blob + H.off_w);
+  const uint16_t* LOC = reinterpret_cast<const uint16_t*>(s_blob + H.off_loc);
   const int t = t0 + lane;
   const TIN* sx0 = sx + lane;
   const TIN* sx1 = sx + (size_t)nCells * S + lane;
@@ -145,32 +208,43 @@ agg_staged_kernel(const AggArgs a) {
     int s = 0;
     if (lane == 0) s = atomicAdd(&s_next, 1);
     s = __shfl_sync(0xffffffffu, s, 0);
-    if (s >= nSeg) break;
-    const int seg = seg0 + s;
-    const int e0 = a.seg_ent_ptr[seg], e1 = a.seg_ent_ptr[seg + 1];
-    const int target = a.seg_target[seg];
+    if (s >= H.n_seg) break;
+    const int4 sg = segs[s];  // {target, e0, n, -}
+    const int target = sg.x;
+    const double den = target >= 0 ? __ldg(a.den + target) : 1.0;  // latency hidden by the loop
     double acc[NOUT];
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) acc[j] = 0.0;
+    const int e_full = sg.y + (sg.z & ~3), e_end = sg.y + sg.z;
 #pragma unroll 2
-    for (int e = e0; e < e1; ++e) {
-      const double w = __ldg(a.ent_w + e);
-      const int loc = __ldg(a.ent_loc + e);
-      const double x0 = (double)sx0[loc * S];
-      double x1 = 0.0;
-      if constexpr (NIN == 2) x1 = (double)sx1[loc * S];
-      double f[NOUT];
-      ctb_apply<KIND, NOUT>(a.tr, x0, x1, f);
-#pragma unroll
-      for (int j = 0; j < NOUT; ++j)
-        if (f[j] == f[j]) acc[j] = fma(w, f[j], acc[j]);  // NaN product skipped (skipna sum)
+    for (int e = sg.y; e < e_full; e += 4) {
+      const uint2 lc = *reinterpret_cast<const uint2*>(LOC + e);
+      const double2 w01 = *reinterpret_cast<const double2*>(W + e);
+      const double2 w23 = *reinterpret_cast<const double2*>(W + e + 2);
+      const int l0 = lc.x & 0xffff, l1 = lc.x >> 16, l2 = lc.y & 0xffff, l3 = lc.y >> 16;
+      TIN r0[4], r1[4];
+      r0[0] = sx0[l0 * S]; r0[1] = sx0[l1 * S]; r0[2] = sx0[l2 * S]; r0[3] = sx0[l3 * S];
+      if constexpr (NIN == 2) {
+        r1[0] = sx1[l0 * S]; r1[1] = sx1[l1 * S]; r1[2] = sx1[l2 * S]; r1[3] = sx1[l3 * S];
+      } else {
+        r1[0] = r1[1] = r1[2] = r1[3] = TIN(0);
+      }
+      accumulate<TIN, KIND, NOUT>(a.tr, w01.x, r0[0], r1[0], acc);
+      accumulate<TIN, KIND, NOUT>(a.tr, w01.y, r0[1], r1[1], acc);
+      accumulate<TIN, KIND, NOUT>(a.tr, w23.x, r0[2], r1[2], acc);
+      accumulate<TIN, KIND, NOUT>(a.tr, w23.y, r0[3], r1[3], acc);
+    }
+    for (int e = e_full; e < e_end; ++e) {  // ragged tail (< 4 entries)
+      const int l = LOC[e];
+      TIN r1 = TIN(0);
+      if constexpr (NIN == 2) r1 = sx1[l * S];
+      accumulate<TIN, KIND, NOUT>(a.tr, W[e], sx0[l * S], r1, acc);
     }
     if (t < a.T) {
       if (target >= 0) {
-        const double d = a.den[target];
 #pragma unroll
         for (int j = 0; j < NOUT; ++j)
-          a.out[((size_t)j * a.R + target) * a.out_ld + t] = acc[j] / d;
+          a.out[((size_t)j * a.R + target) * a.out_ld + t] = acc[j] / den;
       } else {
         const int slot = ~target;
 #pragma unroll
@@ -225,11 +299,7 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(const AggArgs a) {
         x0 = (double)__ldg(X0 + off);
         if constexpr (NIN == 2) x1 = (double)__ldg(X1 + off);
       }
-      double f[NOUT];
-      ctb_apply<KIND, NOUT>(a.tr, x0, x1, f);
-#pragma unroll
-      for (int j = 0; j < NOUT; ++j)
-        if (f[j] == f[j]) acc[j] = fma(w, f[j], acc[j]);
+      accumulate<double, KIND, NOUT>(a.tr, w, x0, x1, acc);
     }
     if (tv) {
       const double d = a.den[r];
@@ -244,7 +314,7 @@ template <typename TIN, int KIND, int NOUT>
 int launch_staged(const ctb_plan* P, const AggArgs& a, bool vec, cudaStream_t st) {
   constexpr int NIN = NIn<KIND>::v;
   const size_t smem = (size_t)NIN * P->info.max_bundle_cells * CTB_S * sizeof(TIN) +
-                      (size_t)(P->info.max_bundle_cells / CTB_PIECE) * sizeof(int);
+                      (size_t)P->info.max_meta_bytes;
   int dev_max = 0;
   CTB_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
   if (smem > (size_t)dev_max) {
@@ -396,8 +466,7 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
   a.x0 = x0; a.x1 = x1; a.stride = stride; a.tix = time_index; a.T = (int)T; a.out_ld = out_ld; a.ncell = P->ncell;
   a.R = P->R; a.out = out; a.scratch = (double*)workspace; a.n_scratch = P->n_scratch;
   a.den = P->d_den; a.b_piece_ptr = P->d_b_piece_ptr; a.pieces = P->d_pieces;
-  a.b_seg_ptr = P->d_b_seg_ptr; a.seg_target = P->d_seg_target; a.seg_ent_ptr = P->d_seg_ent_ptr;
-  a.ent_w = P->d_ent_w; a.ent_loc = P->d_ent_loc; a.row_ptr = P->d_row_ptr; a.col = P->d_col;
+  a.b_blob_off = P->d_b_blob_off; a.blob = P->d_blob; a.row_ptr = P->d_row_ptr; a.col = P->d_col;
   a.w = P->d_w; a.split_region = P->d_split_region; a.split_slot_ptr = P->d_split_slot_ptr;
   a.n_split = P->n_split;
   const size_t es = dtype == CTB_F32 ? 4 : 8;

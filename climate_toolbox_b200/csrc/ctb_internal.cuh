@@ -39,6 +39,19 @@ constexpr int CTB_S = CTB_TB + 1;      // smem row stride in elements: odd => co
 constexpr int CTB_PIECE = 4;           // gridcells per staged piece (16 B of f32)
 constexpr int CTB_STAGE_THREADS = 256; // 8 warps: each stages 4 days x 8 pieces per step
 
+// Per-bundle metadata blob, copied to shared memory with one cp.async.bulk:
+//   [CtbBlobHeader][n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint16 loc]
+struct CtbBlobHeader {
+  int32_t n_seg, n_ent_pad;
+  int32_t off_w, off_loc;  // byte offsets from the blob start (16 B aligned)
+};
+struct CtbSeg {
+  int32_t target;  // >= 0: region row of `out`; < 0: ~scratch_slot (region split over bundles)
+  int32_t e0;      // first entry (multiple of 4)
+  int32_t n;       // entries
+  int32_t pad_;
+};
+
 // -------------------------------------------------------------- the plan ---
 struct ctb_plan {
   int device = 0;
@@ -57,11 +70,8 @@ struct ctb_plan {
   int32_t n_bundles = 0, n_segments = 0;
   int32_t* d_b_piece_ptr = nullptr;  // [n_bundles+1] -> d_pieces
   int32_t* d_pieces = nullptr;       // global piece index (cell / 4), ascending per bundle
-  int32_t* d_b_seg_ptr = nullptr;    // [n_bundles+1] -> segments
-  int32_t* d_seg_target = nullptr;   // >=0: region row of `out`; <0: ~scratch_slot
-  int32_t* d_seg_ent_ptr = nullptr;  // [n_segments+1] -> entries
-  double* d_ent_w = nullptr;         // [n_entries]
-  uint16_t* d_ent_loc = nullptr;     // [n_entries] local staged cell
+  int64_t* d_b_blob_off = nullptr;   // [n_bundles+1] byte offsets into d_blob (16 B aligned)
+  uint8_t* d_blob = nullptr;         // per-bundle metadata blobs, see CtbBlobHeader
   // regions split over several bundles: out[r] = sum(scratch[slot0..slot1)) / den[r]
   int32_t n_split = 0, n_scratch = 0;
   int32_t* d_split_region = nullptr;  // [n_split]

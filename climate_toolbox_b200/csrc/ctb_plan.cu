@@ -121,17 +121,41 @@ uint64_t hilbert_xy2d(uint32_t n, uint32_t x, uint32_t y) {
   return d;
 }
 
+// Per-bundle metadata blob (16-byte aligned, fetched into shared memory by ONE bulk
+// async copy while the tile is being staged):
+//   [CtbBlobHeader][n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint16 loc]
+// every segment's entries start at a multiple of 4 (vector LDS in the gather loop).
 struct BundleBuilder {
-  // flat outputs
-  std::vector<int32_t> b_piece_ptr{0}, pieces, b_seg_ptr{0}, seg_target, seg_ent_ptr{0};
-  std::vector<double> ent_w;
-  std::vector<uint16_t> ent_loc;
-  int32_t max_cells = 0;
+  std::vector<int32_t> b_piece_ptr{0}, pieces;
+  std::vector<int64_t> b_blob_off{0};
+  std::vector<uint8_t> blob;
+  int32_t max_cells = 0, max_meta = 0, n_segments = 0;
+  int32_t bytes_cd = 4;  // staged bytes per cell-day
+  int32_t budget = 0;
 
-  // current bundle under construction
+  // bundle under construction
   std::vector<int32_t> cur_pieces;  // unsorted, unique
   struct Seg { int32_t target; std::vector<int32_t> cols; std::vector<double> ws; };
   std::vector<Seg> cur_segs;
+  int32_t cur_ent_pad = 0;
+
+  static int32_t pad(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
+  static int32_t meta_bytes(int32_t n_pieces, int32_t n_seg, int32_t n_ent_pad) {
+    return pad(n_pieces * 4, 16) + (int32_t)sizeof(CtbBlobHeader) + n_seg * (int32_t)sizeof(CtbSeg) +
+           10 * pad(n_ent_pad, 8);
+  }
+  int32_t total_bytes(int32_t n_pieces, int32_t n_seg, int32_t n_ent_pad) const {
+    return n_pieces * CTB_PIECE * CTB_S * bytes_cd + meta_bytes(n_pieces, n_seg, n_ent_pad);
+  }
+  bool fits(int32_t extra_pieces, int32_t extra_ent) const {
+    return total_bytes((int32_t)cur_pieces.size() + extra_pieces, (int32_t)cur_segs.size() + 1,
+                       cur_ent_pad + pad(extra_ent, 4)) <= budget &&
+           ((int32_t)cur_pieces.size() + extra_pieces) * CTB_PIECE <= 65532;
+  }
+  void add(Seg&& s) {
+    cur_ent_pad += pad((int32_t)s.cols.size(), 4);
+    cur_segs.push_back(std::move(s));
+  }
 
   void close() {
     if (cur_segs.empty()) return;
@@ -139,23 +163,39 @@ struct BundleBuilder {
     // LPT order: longest segments first (warps fetch segments dynamically)
     std::stable_sort(cur_segs.begin(), cur_segs.end(),
                      [](const Seg& a, const Seg& b) { return a.cols.size() > b.cols.size(); });
-    for (const Seg& s : cur_segs) {
-      seg_target.push_back(s.target);
+    const int32_t n_seg = (int32_t)cur_segs.size();
+    const int32_t n_ent_pad = pad(cur_ent_pad, 8);
+    CtbBlobHeader h{n_seg, n_ent_pad, (int32_t)sizeof(CtbBlobHeader) + n_seg * (int32_t)sizeof(CtbSeg), 0};
+    h.off_loc = h.off_w + 8 * n_ent_pad;
+    const size_t base = blob.size();
+    const size_t bytes = (size_t)pad(h.off_loc + 2 * n_ent_pad, 16);
+    blob.resize(base + bytes, 0);
+    std::memcpy(&blob[base], &h, sizeof h);
+    CtbSeg* segs = reinterpret_cast<CtbSeg*>(&blob[base + sizeof h]);
+    double* w = reinterpret_cast<double*>(&blob[base + h.off_w]);
+    uint16_t* loc = reinterpret_cast<uint16_t*>(&blob[base + h.off_loc]);
+    int32_t e = 0;
+    for (int32_t i = 0; i < n_seg; ++i) {
+      const Seg& s = cur_segs[i];
+      segs[i] = CtbSeg{s.target, e, (int32_t)s.cols.size(), 0};
       for (size_t k = 0; k < s.cols.size(); ++k) {
         const int32_t piece = s.cols[k] / CTB_PIECE;
         const int32_t lp = (int32_t)(std::lower_bound(cur_pieces.begin(), cur_pieces.end(), piece) -
                                      cur_pieces.begin());
-        ent_loc.push_back((uint16_t)(lp * CTB_PIECE + s.cols[k] % CTB_PIECE));
-        ent_w.push_back(s.ws[k]);
+        loc[e + k] = (uint16_t)(lp * CTB_PIECE + s.cols[k] % CTB_PIECE);
+        w[e + k] = s.ws[k];
       }
-      seg_ent_ptr.push_back((int32_t)ent_w.size());
+      e += pad((int32_t)s.cols.size(), 4);
     }
     pieces.insert(pieces.end(), cur_pieces.begin(), cur_pieces.end());
     b_piece_ptr.push_back((int32_t)pieces.size());
-    b_seg_ptr.push_back((int32_t)seg_target.size());
+    b_blob_off.push_back((int64_t)blob.size());
+    n_segments += n_seg;
     max_cells = std::max<int32_t>(max_cells, (int32_t)cur_pieces.size() * CTB_PIECE);
+    max_meta = std::max<int32_t>(max_meta, meta_bytes((int32_t)cur_pieces.size(), n_seg, n_ent_pad));
     cur_pieces.clear();
     cur_segs.clear();
+    cur_ent_pad = 0;
   }
 };
 
@@ -175,9 +215,8 @@ extern "C" void ctb_plan_free(ctb_plan* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->d_row_cell); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_w);
-  cudaFree(p->d_den); cudaFree(p->d_b_piece_ptr); cudaFree(p->d_pieces); cudaFree(p->d_b_seg_ptr);
-  cudaFree(p->d_seg_target); cudaFree(p->d_seg_ent_ptr); cudaFree(p->d_ent_w);
-  cudaFree(p->d_ent_loc); cudaFree(p->d_split_region); cudaFree(p->d_split_slot_ptr);
+  cudaFree(p->d_den); cudaFree(p->d_b_piece_ptr); cudaFree(p->d_pieces); cudaFree(p->d_b_blob_off);
+  cudaFree(p->d_blob); cudaFree(p->d_split_region); cudaFree(p->d_split_slot_ptr);
   cudaSetDevice(prev);
   delete p;
 }
@@ -345,15 +384,14 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
 
   // ---- staging bundles ----
   int32_t bytes_cd = opts && opts->stage_bytes_per_cell_day > 0 ? opts->stage_bytes_per_cell_day : 4;
-  int32_t budget = opts && opts->smem_budget_bytes > 0 ? opts->smem_budget_bytes : 72 * 1024;
-  int32_t cap_cells = budget / (CTB_S * bytes_cd);
-  cap_cells -= cap_cells % CTB_PIECE;
-  cap_cells = std::min(cap_cells, 65536 - CTB_PIECE);
-  if (cap_cells < 2 * CTB_PIECE) {
+  int32_t budget = opts && opts->smem_budget_bytes > 0 ? opts->smem_budget_bytes : 74 * 1024;
+  BundleBuilder B;
+  B.bytes_cd = bytes_cd;
+  B.budget = budget;
+  if (B.total_bytes(2, 1, 8) > budget) {
     ctb_set_error("ctb_plan_build: smem budget %d too small", budget);
     return CTB_ERR_INVALID;
   }
-  const int32_t cap_pieces = cap_cells / CTB_PIECE;
 
   uint32_t hn = 1;
   while ((int32_t)hn < std::max(nlat_phys, nlon_phys)) hn <<= 1;
@@ -384,7 +422,6 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   std::vector<uint8_t> seen(npiece_grid, 0);     // piece referenced at all
   std::vector<uint8_t> cell_seen(ncell, 0);
   int32_t gen = 0;
-  BundleBuilder B;
   std::vector<int32_t> split_region, split_slot_ptr{0};
   int32_t n_scratch = 0;
   std::vector<int32_t> newp;
@@ -398,7 +435,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
       const int32_t p = cols[k] / CTB_PIECE;
       if (stamp[p] != gen) { stamp[p] = gen; B.cur_pieces.push_back(p); }
     }
-    B.cur_segs.push_back(std::move(s));
+    B.add(std::move(s));
   };
 
   for (const Region& g : regs) {
@@ -411,7 +448,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
     }
     std::sort(newp.begin(), newp.end());
     newp.erase(std::unique(newp.begin(), newp.end()), newp.end());
-    if ((int32_t)(B.cur_pieces.size() + newp.size()) <= cap_pieces) {
+    if (B.fits((int32_t)newp.size(), n)) {
       add_segment(g.r, &col[g.e0], &w[g.e0], n);
       continue;
     }
@@ -423,11 +460,11 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
     own.erase(std::unique(own.begin(), own.end()), own.end());
     B.close();
     ++gen;
-    if ((int32_t)own.size() <= cap_pieces) {
+    if (B.fits((int32_t)own.size(), n)) {
       add_segment(g.r, &col[g.e0], &w[g.e0], n);
       continue;
     }
-    // split: order the region's rows by cell, cut into fragments of <= cap pieces
+    // split: order the region's rows by cell, cut into fragments that fit one tile
     std::vector<int32_t> idx(n);
     std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(),
@@ -447,11 +484,10 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
     for (int32_t q = 0; q < n; ++q) {
       const int32_t c = col[g.e0 + idx[q]];
       const int32_t p = c / CTB_PIECE;
-      if (p != last_piece) {
-        if (fpieces == cap_pieces) flush();
-        ++fpieces;
-        last_piece = p;
-      }
+      const int32_t np = fpieces + (p != last_piece ? 1 : 0);
+      if (!fc.empty() && B.total_bytes(np, 1, BundleBuilder::pad((int32_t)fc.size() + 1, 4)) > budget)
+        flush();
+      if (p != last_piece) { ++fpieces; last_piece = p; }
       fc.push_back(c);
       fw.push_back(w[g.e0 + idx[q]]);
     }
@@ -477,15 +513,12 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   if ((rc = upload(&P->d_w, w))) return rc;
   if ((rc = upload(&P->d_b_piece_ptr, B.b_piece_ptr))) return rc;
   if ((rc = upload(&P->d_pieces, B.pieces))) return rc;
-  if ((rc = upload(&P->d_b_seg_ptr, B.b_seg_ptr))) return rc;
-  if ((rc = upload(&P->d_seg_target, B.seg_target))) return rc;
-  if ((rc = upload(&P->d_seg_ent_ptr, B.seg_ent_ptr))) return rc;
-  if ((rc = upload(&P->d_ent_w, B.ent_w))) return rc;
-  if ((rc = upload(&P->d_ent_loc, B.ent_loc))) return rc;
+  if ((rc = upload(&P->d_b_blob_off, B.b_blob_off))) return rc;
+  if ((rc = upload(&P->d_blob, B.blob))) return rc;
   if ((rc = upload(&P->d_split_region, split_region))) return rc;
   if ((rc = upload(&P->d_split_slot_ptr, split_slot_ptr))) return rc;
   P->n_bundles = (int32_t)B.b_piece_ptr.size() - 1;
-  P->n_segments = (int32_t)B.seg_target.size();
+  P->n_segments = B.n_segments;
   P->n_split = (int32_t)split_region.size();
   P->n_scratch = n_scratch;
 
@@ -493,7 +526,8 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   I.n_rows = n_rows; I.nnz = P->nnz; I.n_cells_distinct = U; I.n_cells_grid = ncell;
   I.n_regions = R; I.n_bundles = P->n_bundles; I.n_pieces = (int64_t)B.pieces.size();
   I.n_pieces_distinct = pieces_distinct; I.n_split_regions = P->n_split;
-  I.n_scratch_slots = n_scratch; I.cap_cells = cap_cells; I.max_bundle_cells = B.max_cells;
+  I.n_scratch_slots = n_scratch; I.cap_cells = budget / (CTB_S * bytes_cd); I.max_bundle_cells = B.max_cells;
+  I.max_meta_bytes = B.max_meta;
   I.time_block = CTB_TB; I.max_region_rows = max_rows;
   CTB_CUDA(cudaDeviceSynchronize());
   return CTB_OK;

@@ -88,6 +88,8 @@ typedef struct ctb_plan_info {
   int32_t max_bundle_cells;
   int32_t time_block;      /* days per staging tile */
   int32_t max_region_rows; /* largest region, in kept rows */
+  int32_t max_meta_bytes;  /* largest per-bundle metadata blob + piece list, bytes */
+  int32_t reserved_;
 } ctb_plan_info;
 
 /* ---- misc ---------------------------------------------------------------- */
