@@ -4,18 +4,24 @@
 // (sum(w*x)/sum(w) per region) with the transforms of
 // climate_toolbox/transformations/transformations.py:69-89,139-141,189 fused in.
 //
-// Staged kernel (TIME_MAJOR input [T][lat][lon], the BCSD layout):
-//   one CTA = one bundle (spatially adjacent regions whose gridcell footprint fits a
-//   shared-memory tile) x one block of 32 days.
+// Fused kernel (TIME_MAJOR input [T][lat][lon], the BCSD layout): one CTA of 16 warps per
+// work item = one bundle (spatially adjacent regions whose gridcell footprint fits a
+// shared-memory tile) x one block of 32 days; two CTAs per SM, so one stages while the
+// other reduces (hardware barriers only -- no polling).
+//   metadata: the bundle's piece list, segment table, weights and staged-cell indices
+//           arrive as ONE bulk async copy (cp.async.bulk, TMA 1-D) signalled on an mbarrier;
 //   stage : 16-byte coalesced global loads of the footprint's 4-cell pieces for 32
-//           day-planes, written TRANSPOSED into smem as a cell-major tile
-//           sx[cell][day] (row stride 33 words => conflict-free both ways);
-//   gather: one warp per region, lane = day; per CSR entry one conflict-free LDS,
-//           fp64 FMA, NaN products skipped; out[r][t] = acc / den[r], 256-byte
-//           coalesced stores along time.
+//           day-planes (8 in flight per thread, 32 warps per SM; shared memory is kept
+//           <= 164 KB per SM because the remaining L1 bounds the loads in flight,
+//           bench_micro/), written TRANSPOSED into smem as a
+//           cell-major tile sx[cell][day] (row stride 33 words => conflict-free both ways);
+//   gather: one warp per region, lane = day; per 4 CSR entries three vector LDS of
+//           metadata + four conflict-free LDS of data, fp64 FMA, NaN products skipped;
+//           out[r][t] = acc / den[r], 256-byte coalesced stores along time.
 // Direct kernel (CELL_MAJOR input [lat][lon][T], or any layout as a fallback):
 //   one warp per (region, 32-day tile), lane = day, coalesced along time.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctb_internal.cuh"
@@ -35,9 +41,17 @@ struct AggArgs {
   double* scratch;
   int n_scratch;
   const double* den;
-  const int32_t *b_piece_ptr, *pieces;
   const int64_t* b_blob_off;
   const unsigned char* blob;
+  int n_bundles;
+  int n_items;
+  const int4* b_desc;
+  int tile_stride;  // bytes between tile stages
+  int meta_b_stride;  // bytes between part-B metadata slots
+  int n_tb;         // time blocks: ceil(T / 32)
+  int chunk_tb;     // time blocks per work unit (a CTA keeps one bundle for a whole unit)
+  int* work_counter; // device counter for dynamic unit scheduling (zeroed per launch)
+  int dbg;          // CTB_DEBUG bits (perf experiments): 1 skip loads, 2 skip STS, 4 skip gather
   const int32_t *row_ptr, *col;
   const double* w;
   const int32_t *split_region, *split_slot_ptr;
@@ -62,23 +76,8 @@ __device__ __forceinline__ double2 ld_stream_d2(const double* p) {
   return v;
 }
 
-// ---- load one 4-cell piece of one day-plane ------------------------------
-template <typename TIN, bool VEC>
-__device__ __forceinline__ void load_piece(const TIN* __restrict__ plane, int piece, int64_t ncell,
-                                           TIN (&v)[4]) {
-  const int64_t c = (int64_t)piece * CTB_PIECE;
-  if constexpr (VEC && sizeof(TIN) == 4) {
-    const float4 q = ld_stream_f4(reinterpret_cast<const float*>(plane + c));
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-  } else if constexpr (VEC) {
-    const double2 q0 = ld_stream_d2(reinterpret_cast<const double*>(plane + c));
-    const double2 q1 = ld_stream_d2(reinterpret_cast<const double*>(plane + c + 2));
-    v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (c + j < ncell) ? __ldg(plane + c + j) : TIN(0);
-  }
-}
+// phase timers for CTB_DEBUG & 16 (perf experiments): sums of clock64 deltas of warp 0
+__device__ unsigned long long g_ctb_timers[8];
 
 // ---- mbarrier + bulk async copy (TMA 1-D; SASS: UBLKCP / SYNCS) ---------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -97,13 +96,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n"
       "@p bra DONE_%=;\n"
+      "nanosleep.u32 128;\n"   // back off: polls occupy the MIO queue the LDS/STS need
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
@@ -111,21 +114,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-template <typename TIN> struct StageUnroll { static constexpr int v = sizeof(TIN) == 4 ? 8 : 4; };
-
 // one CSR entry: acc_j += w * f_j(x), NaN products skipped (skipna sum, aggregations.py:78)
 template <typename TIN, int KIND, int NOUT>
 __device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TIN r1,
                                            double (&acc)[NOUT]) {
   double f[NOUT];
-  ctb_apply<KIND, NOUT>(tr, (double)r0, (double)r1, f);
-  if constexpr (KIND == CTB_TR_IDENTITY || KIND == CTB_TR_POLY) {
-    // f is NaN iff x is NaN: one compare in the storage type gates all outputs
-    if (r0 == r0) {
+  if constexpr (KIND == CTB_TR_IDENTITY) {
+    // the product is NaN iff x is NaN (w is finite, non-zero): zero it in the storage type
+    const TIN xs = (r0 == r0) ? r0 : TIN(0);
+    acc[0] = fma(w, (double)xs, acc[0]);
+  } else if constexpr (KIND == CTB_TR_POLY) {
+    ctb_apply<KIND, NOUT>(tr, (double)r0, (double)r1, f);
+    if (r0 == r0) {   // f is NaN iff x is NaN: one compare gates all outputs
 #pragma unroll
       for (int j = 0; j < NOUT; ++j) acc[j] = fma(w, f[j], acc[j]);
     }
   } else {
+    ctb_apply<KIND, NOUT>(tr, (double)r0, (double)r1, f);
 #pragma unroll
     for (int j = 0; j < NOUT; ++j)
       if (f[j] == f[j]) acc[j] = fma(w, f[j], acc[j]);
@@ -133,91 +138,149 @@ __device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TI
 }
 
 template <typename TIN, int KIND, int NOUT, bool VEC>
-__global__ void __launch_bounds__(CTB_STAGE_THREADS, 3)
-agg_staged_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(CTB_THREADS, CTB_CTAS_PER_SM)
+agg_fused_kernel(const AggArgs a) {
   constexpr int NIN = NIn<KIND>::v;
   constexpr int S = CTB_S;
-  constexpr int UNR = StageUnroll<TIN>::v;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_next;
+  constexpr int HALVES = sizeof(TIN) / 4;       // 16-byte units per piece-day of one input
+  constexpr int CPU = 16 / sizeof(TIN);          // cells per unit
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
-
-  const int b = blockIdx.x;
-  const int t0 = blockIdx.y * CTB_TB;
-  const int p0 = a.b_piece_ptr[b];
-  const int nP = a.b_piece_ptr[b + 1] - p0;
-  const int nCells = nP * CTB_PIECE;
-  const int64_t blob0 = a.b_blob_off[b];
-  const uint32_t blob_bytes = (uint32_t)(a.b_blob_off[b + 1] - blob0);
-  TIN* sx = reinterpret_cast<TIN*>(smem_raw);                     // [NIN][nCells][S]
-  int* s_piece = reinterpret_cast<int*>(sx + (size_t)NIN * nCells * S);
-  unsigned char* s_blob = reinterpret_cast<unsigned char*>(s_piece) + ((nP * 4 + 15) & ~15);
+  __shared__ int s_unit;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    s_next = 0;
-    mbar_init(&s_bar, 1);
-    // segment table + weights + staged-cell indices: one bulk copy, lands during staging
-    bulk_g2s(s_blob, a.blob + blob0, blob_bytes, &s_bar);
-  }
-  for (int i = tid; i < nP; i += CTB_STAGE_THREADS) s_piece[i] = a.pieces[p0 + i];
-  __syncthreads();
+  unsigned char* const s_blob = smem_raw + a.tile_stride;
+  if (tid == 0) mbar_init(&s_bar, 1);
 
-  // ---------------- stage: [day][piece] global  ->  [cell][day] shared ----------------
+  // Work unit = (bundle, chunk of `chunk_tb` consecutive 32-day blocks), handed out by an
+  // atomic counter in chunk-major order: CTAs running together work on neighbouring bundles
+  // of the same days (shared lines meet in L2), and the bundle's metadata is fetched once
+  // per unit.  While a tile is staged, the same footprint of the NEXT block is prefetched
+  // into L2, so all but the first tile of a unit read L2-resident data.
+  long long tm[6] = {0, 0, 0, 0, 0, 0};
+  long long c0 = clock64();
+  auto lap = [&](int i) { const long long c1 = clock64(); tm[i] += c1 - c0; c0 = c1; };
+  for (int n_done = 0;; ++n_done) {
+  __syncthreads();   // previous unit fully reduced: tile, blob and s_unit may be reused
+  if (tid == 0) {
+    s_unit = atomicAdd(a.work_counter, 1);
+    if (s_unit < a.n_items) {
+      const int4 d = __ldg(a.b_desc + s_unit % a.n_bundles);
+      const int64_t o = ((int64_t)(uint32_t)d.y << 32) | (uint32_t)d.x;
+      bulk_g2s(s_blob, a.blob + o, (uint32_t)(d.z + d.w), &s_bar);
+    }
+  }
+  __syncthreads();
+  const int unit = s_unit;
+  if (unit >= a.n_items) break;
+  const int tb_begin = (unit / a.n_bundles) * a.chunk_tb;
+  const int tb_end = min(tb_begin + a.chunk_tb, a.n_tb);
+  mbar_wait(&s_bar, n_done & 1);
+  lap(0);   // unit fetch + metadata
+  const CtbBlobHeader H = *reinterpret_cast<const CtbBlobHeader*>(s_blob);
+  const int* s_piece = reinterpret_cast<const int*>(s_blob + sizeof(CtbBlobHeader));
+  const unsigned char* mb = s_blob + H.bytes_a;
+  const int nP = H.n_pieces;
+
+  for (int tb = tb_begin; tb < tb_end; ++tb) {
+  const int t0 = tb * CTB_TB;
+  if (tb != tb_begin) __syncthreads();   // tile buffer free again
+  lap(1);   // waiting for the other warps' gather
+  // ---------------- stage: [day][piece] global  ->  [input][cell][day] shared -------------
   {
     const int l8 = lane & 7, l4 = lane >> 3;
-    const int dl = warp * 4 + l4;  // 8 warps x 4 days = CTB_TB
+    const int dl = (warp & 7) * 4 + l4;            // day within the tile
+    constexpr int NSUB = CTB_WARPS / 8;            // warps sharing one 4-day group
+    const int sub = warp >> 3;
     const int t = t0 + dl;
-    if (t < a.T) {
+    const int n_units = nP * HALVES * NIN;         // unit index: [input][piece][half]
+    if (t < a.T && !(a.dbg & 1)) {
       const int64_t tp = a.tix ? a.tix[t] : t;
+      const TIN* p0 = reinterpret_cast<const TIN*>(a.x0) + tp * a.stride;
+      const TIN* p1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) + tp * a.stride : p0;
+      // the same footprint one time block later: prefetched into L2 now, staged next iteration
+      const int tn = t + CTB_TB;
+      const bool pf = tn < a.T && tb + 1 < tb_end && !(a.dbg & 8);
+      const int64_t pf_delta = pf ? ((a.tix ? (int64_t)a.tix[tn] : (int64_t)tn) - tp) * a.stride : 0;
+      TIN* sx = reinterpret_cast<TIN*>(smem_raw) + dl;
+      for (int g0 = l8 + 8 * sub; g0 < n_units; g0 += 8 * NSUB * CTB_LOADS) {
+        int off[CTB_LOADS];
+        uint32_t v[CTB_LOADS][4];
 #pragma unroll
-      for (int in = 0; in < NIN; ++in) {
-        const TIN* plane = reinterpret_cast<const TIN*>(in ? a.x1 : a.x0) + tp * a.stride;
-        TIN* sd = sx + (size_t)in * nCells * S + dl;
-        for (int pg = l8; pg < nP; pg += 8 * UNR) {
-          TIN v[UNR][4];
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            const int q = pg + 8 * u;
-            if (q < nP) load_piece<TIN, VEC>(plane, s_piece[q], a.ncell, v[u]);
+        for (int u = 0; u < CTB_LOADS; ++u) {      // all index reads first, then all loads
+          const int g = g0 + 8 * NSUB * u;
+          off[u] = -1;
+          if (g < n_units) {
+            const int in = g / (nP * HALVES), r = g - in * (nP * HALVES);
+            off[u] = (s_piece[r / HALVES] * CTB_PIECE + (r % HALVES) * CPU) | (in << 30);
           }
+        }
 #pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            const int q = pg + 8 * u;
-            if (q < nP) {
+        for (int u = 0; u < CTB_LOADS; ++u) {
+          if (off[u] >= 0) {
+            const int o = off[u] & ~(1 << 30);
+            const TIN* src = (NIN == 2 && (off[u] >> 30)) ? p1 + o : p0 + o;
+            if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + pf_delta));
+            if constexpr (VEC) {
+              asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "l"(src));
+            } else {
+              TIN tv[CPU];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) sd[(q * CTB_PIECE + j) * S] = v[u][j];
+              for (int q = 0; q < CPU; ++q) tv[q] = (o + q < a.ncell) ? __ldg(src + q) : TIN(0);
+              if constexpr (sizeof(TIN) == 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[u][q] = __float_as_uint((float)tv[q]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const long long bb = __double_as_longlong((double)tv[q]);
+                  v[u][2 * q] = (uint32_t)bb; v[u][2 * q + 1] = (uint32_t)(bb >> 32);
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < CTB_LOADS; ++u) {
+          const int g = g0 + 8 * NSUB * u;
+          if (off[u] >= 0 && !(a.dbg & 2)) {
+            // unit g covers cells [g*CPU, g*CPU + CPU) of the [input][cell] row space
+            TIN* sd = sx + (size_t)g * CPU * S;
+            if constexpr (sizeof(TIN) == 4) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) sd[q * S] = __uint_as_float(v[u][q]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                sd[q * S] = __longlong_as_double(((long long)v[u][2 * q + 1] << 32) | v[u][2 * q]);
             }
           }
         }
       }
     }
   }
+  lap(2);   // own staging (loads + transposed stores)
   __syncthreads();
-  mbar_wait(&s_bar, 0);
+  lap(3);   // waiting for the other warps' staging
 
-  // ---------------- gather + segmented weighted sum: warp = region, lane = day --------
-  const CtbBlobHeader H = *reinterpret_cast<const CtbBlobHeader*>(s_blob);
-  const int4* segs = reinterpret_cast<const int4*>(s_blob + sizeof(CtbBlobHeader));
-  const double* W = reinterpret_cast<const double*>(s_blob + H.off_w);
-  const uint16_t* LOC = reinterpret_cast<const uint16_t*>(s_blob + H.off_loc);
+  // ---------------- gather + segmented weighted sum: warp = region, lane = day ------------
+  const CtbSeg* segs = reinterpret_cast<const CtbSeg*>(mb + H.off_seg);
+  const double* W = reinterpret_cast<const double*>(mb + H.off_w);
+  const uint16_t* LOC = reinterpret_cast<const uint16_t*>(mb + H.off_loc);
+  const TIN* sx0 = reinterpret_cast<const TIN*>(smem_raw) + lane;
+  const TIN* sx1 = sx0 + (size_t)nP * CTB_PIECE * S;
   const int t = t0 + lane;
-  const TIN* sx0 = sx + lane;
-  const TIN* sx1 = sx + (size_t)nCells * S + lane;
-  for (;;) {
-    int s = 0;
-    if (lane == 0) s = atomicAdd(&s_next, 1);
-    s = __shfl_sync(0xffffffffu, s, 0);
-    if (s >= H.n_seg) break;
-    const int4 sg = segs[s];  // {target, e0, n, -}
-    const int target = sg.x;
-    const double den = target >= 0 ? __ldg(a.den + target) : 1.0;  // latency hidden by the loop
-    double acc[NOUT];
+  // segments are sorted longest-first: round-robin over the warps is balanced
+  for (int s = warp; s < ((a.dbg & 4) ? 0 : H.n_seg); s += CTB_WARPS) {
+    const CtbSeg sg = segs[s];
+    double acc[NOUT], acc2[NOUT];
 #pragma unroll
-    for (int j = 0; j < NOUT; ++j) acc[j] = 0.0;
-    const int e_full = sg.y + (sg.z & ~3), e_end = sg.y + sg.z;
+    for (int j = 0; j < NOUT; ++j) acc[j] = acc2[j] = 0.0;
+    const int e0 = (int)sg.e0_4 * 4;
+    const int e_full = e0 + ((int)sg.n & ~3), e_end = e0 + (int)sg.n;
 #pragma unroll 2
-    for (int e = sg.y; e < e_full; e += 4) {
+    for (int e = e0; e < e_full; e += 4) {
       const uint2 lc = *reinterpret_cast<const uint2*>(LOC + e);
       const double2 w01 = *reinterpret_cast<const double2*>(W + e);
       const double2 w23 = *reinterpret_cast<const double2*>(W + e + 2);
@@ -230,9 +293,9 @@ agg_staged_kernel(const AggArgs a) {
         r1[0] = r1[1] = r1[2] = r1[3] = TIN(0);
       }
       accumulate<TIN, KIND, NOUT>(a.tr, w01.x, r0[0], r1[0], acc);
-      accumulate<TIN, KIND, NOUT>(a.tr, w01.y, r0[1], r1[1], acc);
+      accumulate<TIN, KIND, NOUT>(a.tr, w01.y, r0[1], r1[1], acc2);
       accumulate<TIN, KIND, NOUT>(a.tr, w23.x, r0[2], r1[2], acc);
-      accumulate<TIN, KIND, NOUT>(a.tr, w23.y, r0[3], r1[3], acc);
+      accumulate<TIN, KIND, NOUT>(a.tr, w23.y, r0[3], r1[3], acc2);
     }
     for (int e = e_full; e < e_end; ++e) {  // ragged tail (< 4 entries)
       const int l = LOC[e];
@@ -241,17 +304,24 @@ agg_staged_kernel(const AggArgs a) {
       accumulate<TIN, KIND, NOUT>(a.tr, W[e], sx0[l * S], r1, acc);
     }
     if (t < a.T) {
-      if (target >= 0) {
+      if (sg.target >= 0) {
 #pragma unroll
         for (int j = 0; j < NOUT; ++j)
-          a.out[((size_t)j * a.R + target) * a.out_ld + t] = acc[j] / den;
+          a.out[((size_t)j * a.R + sg.target) * a.out_ld + t] = (acc[j] + acc2[j]) * sg.rden;
       } else {
-        const int slot = ~target;
+        const int slot_o = ~sg.target;
 #pragma unroll
         for (int j = 0; j < NOUT; ++j)
-          a.scratch[((size_t)j * a.n_scratch + slot) * a.T + t] = acc[j];
+          a.scratch[((size_t)j * a.n_scratch + slot_o) * a.T + t] = acc[j] + acc2[j];
       }
     }
+  }
+  lap(4);   // own gather
+  }   // tiles of the unit
+  }   // units
+  if ((a.dbg & 16) && warp == 0 && lane == 0) {
+    for (int i = 0; i < 5; ++i) atomicAdd(&g_ctb_timers[i], (unsigned long long)tm[i]);
+    atomicAdd(&g_ctb_timers[5], 1ull);
   }
 }
 
@@ -311,27 +381,42 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(const AggArgs a) {
 
 // ------------------------------------------------------------- dispatch -----
 template <typename TIN, int KIND, int NOUT>
-int launch_staged(const ctb_plan* P, const AggArgs& a, bool vec, cudaStream_t st) {
+int launch_staged(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
   constexpr int NIN = NIn<KIND>::v;
-  const size_t smem = (size_t)NIN * P->info.max_bundle_cells * CTB_S * sizeof(TIN) +
-                      (size_t)P->info.max_meta_bytes;
+  const size_t tile = ((size_t)NIN * P->info.max_bundle_cells * CTB_S * sizeof(TIN) + 127) & ~(size_t)127;
+  const size_t meta = (size_t)CTB_META_A_CAP + (((size_t)P->info.max_meta_bytes + 15) & ~(size_t)15);
+  const size_t smem = tile + meta;
   int dev_max = 0;
   CTB_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
+  const size_t units = (size_t)NIN * (P->info.max_bundle_cells / CTB_PIECE) * (sizeof(TIN) / 4);
   if (smem > (size_t)dev_max) {
-    ctb_set_error("staging tile of %zu bytes exceeds the device limit %d: rebuild the plan with "
-                  "stage_bytes_per_cell_day=%d", smem, dev_max, (int)(NIN * sizeof(TIN)));
+    ctb_set_error("staging tile (%zu bytes, %zu units) exceeds the kernel limits: rebuild the plan "
+                  "with stage_bytes_per_cell_day=%d", smem, units, (int)(NIN * sizeof(TIN)));
     return CTB_ERR_UNSUPPORTED;
   }
-  const dim3 grid(P->n_bundles, (a.T + CTB_TB - 1) / CTB_TB);
-  if (P->n_bundles > 0 && a.T > 0) {
+  const int n_tb = (a.T + CTB_TB - 1) / CTB_TB;
+  int chunk_tb = 8;
+  if (const char* e = getenv("CTB_CHUNK_TB")) chunk_tb = std::max(1, atoi(e));
+  const int n_chunks = (n_tb + chunk_tb - 1) / std::max(chunk_tb, 1);
+  chunk_tb = n_chunks ? (n_tb + n_chunks - 1) / n_chunks : 1;   // even chunks
+  const int64_t n_units = (int64_t)P->n_bundles * n_chunks;
+  if (n_units >= (1ll << 31)) { ctb_set_error("too many work units"); return CTB_ERR_UNSUPPORTED; }
+  a.n_bundles = P->n_bundles; a.n_items = (int)n_units; a.n_tb = n_tb; a.chunk_tb = std::max(chunk_tb, 1);
+  a.tile_stride = (int)tile; a.meta_b_stride = 0; a.work_counter = P->d_work_counter;
+  { const char* e = getenv("CTB_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+  if (n_units > 0) {
+    int n_sm = 0;
+    CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
+    const unsigned grid = (unsigned)std::min<int64_t>(n_units, (int64_t)n_sm * CTB_CTAS_PER_SM);
+    CTB_CUDA(cudaMemsetAsync(P->d_work_counter, 0, sizeof(int), st));
     if (vec) {
-      auto k = agg_staged_kernel<TIN, KIND, NOUT, true>;
+      auto k = agg_fused_kernel<TIN, KIND, NOUT, true>;
       CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, CTB_STAGE_THREADS, smem, st>>>(a);
+      k<<<grid, CTB_THREADS, smem, st>>>(a);
     } else {
-      auto k = agg_staged_kernel<TIN, KIND, NOUT, false>;
+      auto k = agg_fused_kernel<TIN, KIND, NOUT, false>;
       CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, CTB_STAGE_THREADS, smem, st>>>(a);
+      k<<<grid, CTB_THREADS, smem, st>>>(a);
     }
     CTB_LAUNCH_CHECK();
   }
@@ -465,8 +550,8 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
   if (prev != P->device) CTB_CUDA(cudaSetDevice(P->device));
   a.x0 = x0; a.x1 = x1; a.stride = stride; a.tix = time_index; a.T = (int)T; a.out_ld = out_ld; a.ncell = P->ncell;
   a.R = P->R; a.out = out; a.scratch = (double*)workspace; a.n_scratch = P->n_scratch;
-  a.den = P->d_den; a.b_piece_ptr = P->d_b_piece_ptr; a.pieces = P->d_pieces;
-  a.b_blob_off = P->d_b_blob_off; a.blob = P->d_blob; a.row_ptr = P->d_row_ptr; a.col = P->d_col;
+  a.den = P->d_den;
+  a.b_blob_off = P->d_b_blob_off; a.blob = P->d_blob; a.b_desc = P->d_b_desc; a.row_ptr = P->d_row_ptr; a.col = P->d_col;
   a.w = P->d_w; a.split_region = P->d_split_region; a.split_slot_ptr = P->d_split_slot_ptr;
   a.n_split = P->n_split;
   const size_t es = dtype == CTB_F32 ? 4 : 8;
@@ -477,4 +562,182 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
                         : run_kind<double>(P, a, layout, variant, vec, transform, n_out, st);
   if (prev != P->device) cudaSetDevice(prev);
   return rc;
+}
+
+// ---------------------------------------------------------------- diagnostics ---
+// Loads-only replay of the streaming kernel's staging traffic on the plan's real
+// footprint (no shared memory, no reduction): measures what the memory system delivers
+// for this access pattern as a function of the lane mapping and loads in flight.
+namespace {
+template <int UNR>
+__global__ void debug_stage_bw_kernel(const float* __restrict__ x, int64_t stride, int T,
+                                      const int64_t* __restrict__ b_blob_off,
+                                      const unsigned char* __restrict__ blob, int n_bundles,
+                                      int n_items, int lanes_p, float* sink, int pf_blocks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lp = lane % lanes_p, ld = lane / lanes_p, dpw = 32 / lanes_p, ndg = 32 / dpw;
+  float acc = 0.f;
+  for (int64_t idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+    const int b = (int)(idx % n_bundles), t0 = (int)(idx / n_bundles) * CTB_TB;
+    const unsigned char* bl = blob + b_blob_off[b];
+    const int nP = reinterpret_cast<const CtbBlobHeader*>(bl)->n_pieces;
+    const int* pieces = reinterpret_cast<const int*>(bl + sizeof(CtbBlobHeader));
+    const int chunks = (nP + lanes_p - 1) / lanes_p, units = chunks * ndg;
+    for (int u0 = warp; u0 < units; u0 += nw * UNR) {
+      float4 v[UNR];
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {
+        const int u = u0 + k * nw;
+        v[k] = make_float4(0, 0, 0, 0);
+        if (u < units) {
+          const int dg = u % ndg, q = (u / ndg) * lanes_p + lp, t = t0 + dg * dpw + ld;
+          if (q < nP && t < T) {
+            const float* src = x + (int64_t)t * stride + (int64_t)__ldg(pieces + q) * 4;
+            // optional L2 prefetch of the same footprint `pf` time blocks ahead
+            if (pf_blocks > 0 && t + pf_blocks * CTB_TB < T)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (int64_t)pf_blocks * CTB_TB * stride));
+            v[k] = ld_stream_f4(src);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) acc += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  }
+  if (acc == 123.25f) *sink = acc;
+}
+}  // namespace
+
+extern "C" int ctb_debug_stage_bw(const ctb_plan* P, const void* x, int64_t stride, int64_t T,
+                                  int lanes_p, int unroll, int warps, int ctas_per_sm, void* sink,
+                                  void* stream) {
+  if (!P || !x || !sink || (lanes_p != 8 && lanes_p != 16 && lanes_p != 32 && lanes_p != 4)) {
+    ctb_set_error("ctb_debug_stage_bw: bad argument");
+    return CTB_ERR_INVALID;
+  }
+  int n_sm = 0;
+  CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
+  if (const char* e = getenv("CTB_L2_FETCH")) {
+    CTB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    static size_t last = 0;
+    if (got != last) { fprintf(stderr, "[ctb] L2 fetch granularity = %zu\n", got); last = got; }
+  }
+  const int64_t n_items = (int64_t)P->n_bundles * ((T + CTB_TB - 1) / CTB_TB);
+  const unsigned grid = (unsigned)std::min<int64_t>(n_items, (int64_t)n_sm * ctas_per_sm);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t dsm = 0;
+  int pf_blocks = 0;
+  if (const char* e = getenv("CTB_DBG_SMEM")) dsm = (size_t)atoi(e);
+  if (const char* e = getenv("CTB_DBG_PF")) pf_blocks = atoi(e);
+#define CTB_DBG(U) if (dsm) CTB_CUDA(cudaFuncSetAttribute(debug_stage_bw_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); debug_stage_bw_kernel<U><<<grid, warps * 32, dsm, st>>>((const float*)x, stride, (int)T, P->d_b_blob_off, P->d_blob, P->n_bundles, (int)n_items, lanes_p, (float*)sink, pf_blocks)
+  switch (unroll) {
+    case 2: CTB_DBG(2); break;
+    case 4: CTB_DBG(4); break;
+    case 8: CTB_DBG(8); break;
+    case 16: CTB_DBG(16); break;
+    default: ctb_set_error("unroll must be 2, 4, 8 or 16"); return CTB_ERR_INVALID;
+  }
+#undef CTB_DBG
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+// cp.async (LDGSTS) replay of the staging traffic: loader warps copy the footprint of item
+// k (pairs of cells x 32 days) straight into a transposed shared-memory tile
+// [cell-group][day][width]; `nbuf` tile buffers in flight; a dummy consumer releases them.
+namespace {
+template <int WIDTH>   // bytes per copy: 4, 8, 16
+__global__ void __launch_bounds__(1024, 1)
+debug_cpasync_bw_kernel(const float* __restrict__ x, int64_t stride, int T,
+                        const int4* __restrict__ b_desc, const unsigned char* __restrict__ blob,
+                        int n_bundles, int n_items, int loader_warps, int nbuf, int buf_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[8], s_empty[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_loader = loader_warps * 32;
+  if (tid == 0) {
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&s_full[i], n_loader); mbar_init(&s_empty[i], 1); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int n_my = n_items > (int)blockIdx.x ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr int CPP = 16 / WIDTH;          // copies per 16-byte piece
+  constexpr int S = CTB_TB + 1;
+  if (warp < loader_warps) {
+    for (int k = 0; k < n_my; ++k) {
+      const int64_t idx = blockIdx.x + (int64_t)k * gridDim.x;
+      const int b = (int)(idx % n_bundles), t0 = (int)(idx / n_bundles) * CTB_TB;
+      const int buf = k % nbuf;
+      if (k >= nbuf) mbar_wait(&s_empty[buf], ((k / nbuf) - 1) & 1);
+      const int4 d = __ldg(b_desc + b);
+      const unsigned char* bl = blob + ((((int64_t)(uint32_t)d.y) << 32) | (uint32_t)d.x);
+      const int nP = reinterpret_cast<const CtbBlobHeader*>(bl)->n_pieces;
+      const int* pieces = reinterpret_cast<const int*>(bl + sizeof(CtbBlobHeader));
+      const int n_units = nP * CPP;         // copies per day
+      const uint32_t sbase = smem_u32(smem_raw + (size_t)buf * buf_bytes);
+      // work = (unit-chunk of 32 lanes, day); warp w takes chunks round-robin
+      const int chunks = (n_units + 31) / 32;
+      for (int w = warp; w < chunks * CTB_TB; w += loader_warps) {
+        const int dday = w % CTB_TB, u = (w / CTB_TB) * 32 + lane, t = t0 + dday;
+        if (u < n_units && t < T) {
+          const int piece = __ldg(pieces + u / CPP);
+          const float* src = x + (int64_t)t * stride + (int64_t)piece * 4 + (u % CPP) * (WIDTH / 4);
+          const uint32_t dst = sbase + (uint32_t)((u * S + dday) * WIDTH);
+          if constexpr (WIDTH == 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          else if constexpr (WIDTH == 8)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+          else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_full[buf])) : "memory");
+    }
+  } else if (warp == loader_warps) {
+    for (int k = 0; k < n_my; ++k) {       // dummy consumer
+      const int buf = k % nbuf;
+      mbar_wait(&s_full[buf], (k / nbuf) & 1);
+      if (lane == 0) mbar_arrive(&s_empty[buf]);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int ctb_debug_cpasync_bw(const ctb_plan* P, const void* x, int64_t stride, int64_t T,
+                                    int width, int loader_warps, int nbuf, void* stream) {
+  if (!P || !x || nbuf < 1 || nbuf > 8 || loader_warps < 1 || loader_warps > 31) {
+    ctb_set_error("ctb_debug_cpasync_bw: bad argument");
+    return CTB_ERR_INVALID;
+  }
+  int n_sm = 0;
+  CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
+  const int64_t n_items = (int64_t)P->n_bundles * ((T + CTB_TB - 1) / CTB_TB);
+  const int buf_bytes = ((P->info.max_bundle_cells * (CTB_TB + 1) * 4) + 127) & ~127;
+  const size_t smem = (size_t)buf_bytes * nbuf;
+  if (smem > 227 * 1024) { ctb_set_error("nbuf too large for the plan's tiles (%zu bytes)", smem); return CTB_ERR_INVALID; }
+  const unsigned grid = (unsigned)std::min<int64_t>(n_items, n_sm);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = (loader_warps + 1) * 32;
+#define CTB_CPA(W)                                                                              \
+  do {                                                                                          \
+    CTB_CUDA(cudaFuncSetAttribute(debug_cpasync_bw_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    debug_cpasync_bw_kernel<W><<<grid, threads, smem, st>>>((const float*)x, stride, (int)T, P->d_b_desc, P->d_blob, \
+                                                          P->n_bundles, (int)n_items, loader_warps, nbuf, buf_bytes); \
+  } while (0)
+  if (width == 16) CTB_CPA(16); else if (width == 8) CTB_CPA(8); else if (width == 4) CTB_CPA(4);
+  else { ctb_set_error("width must be 4, 8 or 16"); return CTB_ERR_INVALID; }
+#undef CTB_CPA
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+extern "C" int ctb_debug_timers(unsigned long long* out8, int reset) {
+  if (out8) CTB_CUDA(cudaMemcpyFromSymbol(out8, g_ctb_timers, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CTB_CUDA(cudaMemcpyToSymbol(g_ctb_timers, z, sizeof z));
+  }
+  return CTB_OK;
 }

@@ -40,17 +40,41 @@ constexpr int CTB_PIECE = 4;           // gridcells per staged piece (16 B of f3
 constexpr int CTB_STAGE_THREADS = 256; // 8 warps: each stages 4 days x 8 pieces per step
 
 // Per-bundle metadata blob, copied to shared memory with one cp.async.bulk:
-//   [CtbBlobHeader][n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint16 loc]
+//   part A: [CtbBlobHeader][n_pieces x int32 piece]
+//   part B: [n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint16 loc]
+// (every section 16-byte aligned; every segment's entries start at a multiple of 4;
+//  off_* are byte offsets from the start of part B)
 struct CtbBlobHeader {
-  int32_t n_seg, n_ent_pad;
-  int32_t off_w, off_loc;  // byte offsets from the blob start (16 B aligned)
+  int32_t n_pieces, n_seg;
+  int32_t off_seg, off_w, off_loc;  // byte offsets from the start of part B
+  int32_t n_ent_pad, bytes_a, bytes_b;
 };
 struct CtbSeg {
   int32_t target;  // >= 0: region row of `out`; < 0: ~scratch_slot (region split over bundles)
-  int32_t e0;      // first entry (multiple of 4)
-  int32_t n;       // entries
-  int32_t pad_;
+  uint16_t e0_4;   // first entry / 4
+  uint16_t n;      // entries
+  double rden;     // 1 / (sum of the region's weights); 1.0 for partial rows.  den == 0 gives
+                   // inf: 0 * inf = NaN and x * inf = +-inf, like 0/0 and x/0
 };
+static_assert(sizeof(CtbBlobHeader) == 32 && sizeof(CtbSeg) == 16, "blob layout");
+
+// fused kernel geometry: CTAs of 16 warps, two per SM.  Every thread stages CTB_LOADS
+// 16-byte loads per tile, so a tile holds CTB_THREADS * CTB_LOADS / 32 = 128 16-byte units
+// per day.  Shared memory is deliberately limited to 164 KB per SM: it is carved out of the
+// L1, and the L1 capacity that is left bounds the loads in flight -- measured
+// (bench_micro/stage_bw3.py): 4.2 TB/s of staging traffic with <= 82 KB per CTA, 2.9 TB/s
+// with 98 KB, 2.1 TB/s with 115 KB.
+constexpr int CTB_THREADS = 512;
+constexpr int CTB_WARPS = CTB_THREADS / 32;
+constexpr int CTB_LOADS = 8;                                      // loads in flight per thread
+constexpr int CTB_TILE_UNITS = CTB_THREADS * CTB_LOADS / CTB_TB;  // 128
+constexpr int CTB_TILE_BYTES = CTB_TILE_UNITS * 4 * CTB_S * 4;    // 67,584 B of shared memory
+constexpr int CTB_CTAS_PER_SM = 2;
+constexpr int CTB_SMEM_PER_CTA = 164 * 1024 / CTB_CTAS_PER_SM - 1024 - 512;  // 82,432 B
+// metadata blob: part A (header + piece list) and part B (segment table + weights +
+// staged-cell indices) are contiguous in global memory and arrive as ONE bulk copy
+constexpr int CTB_META_A_CAP = 32 + CTB_TILE_UNITS * 4;
+constexpr int CTB_META_B_CAP = (CTB_SMEM_PER_CTA - CTB_TILE_BYTES - CTB_META_A_CAP) & ~15;
 
 // -------------------------------------------------------------- the plan ---
 struct ctb_plan {
@@ -68,9 +92,10 @@ struct ctb_plan {
 
   // staging bundles (device)
   int32_t n_bundles = 0, n_segments = 0;
-  int32_t* d_b_piece_ptr = nullptr;  // [n_bundles+1] -> d_pieces
-  int32_t* d_pieces = nullptr;       // global piece index (cell / 4), ascending per bundle
   int64_t* d_b_blob_off = nullptr;   // [n_bundles+1] byte offsets into d_blob (16 B aligned)
+  int4* d_b_desc = nullptr;          // [n_bundles] {off_lo, off_hi, bytes_a, bytes_b}
+  int* d_work_counter = nullptr;     // dynamic unit scheduler of the fused kernel (zeroed per launch;
+                                     // concurrent launches on one plan must share a stream)
   uint8_t* d_blob = nullptr;         // per-bundle metadata blobs, see CtbBlobHeader
   // regions split over several bundles: out[r] = sum(scratch[slot0..slot1)) / den[r]
   int32_t n_split = 0, n_scratch = 0;

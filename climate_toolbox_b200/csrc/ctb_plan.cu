@@ -121,17 +121,17 @@ uint64_t hilbert_xy2d(uint32_t n, uint32_t x, uint32_t y) {
   return d;
 }
 
-// Per-bundle metadata blob (16-byte aligned, fetched into shared memory by ONE bulk
-// async copy while the tile is being staged):
-//   [CtbBlobHeader][n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint16 loc]
-// every segment's entries start at a multiple of 4 (vector LDS in the gather loop).
+// Builds the per-bundle metadata blobs (layout: CtbBlobHeader in ctb_internal.cuh).
 struct BundleBuilder {
-  std::vector<int32_t> b_piece_ptr{0}, pieces;
   std::vector<int64_t> b_blob_off{0};
+  std::vector<int4> desc;
   std::vector<uint8_t> blob;
   int32_t max_cells = 0, max_meta = 0, n_segments = 0;
-  int32_t bytes_cd = 4;  // staged bytes per cell-day
-  int32_t budget = 0;
+  int64_t n_pieces_total = 0;
+  int32_t bytes_cd = 4;       // staged bytes per cell-day
+  int32_t tile_cap = 0;       // bytes of one staging tile
+  int32_t meta_cap = 0;       // bytes of one metadata slot
+  const double* den = nullptr;
 
   // bundle under construction
   std::vector<int32_t> cur_pieces;  // unsorted, unique
@@ -140,17 +140,22 @@ struct BundleBuilder {
   int32_t cur_ent_pad = 0;
 
   static int32_t pad(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
-  static int32_t meta_bytes(int32_t n_pieces, int32_t n_seg, int32_t n_ent_pad) {
-    return pad(n_pieces * 4, 16) + (int32_t)sizeof(CtbBlobHeader) + n_seg * (int32_t)sizeof(CtbSeg) +
-           10 * pad(n_ent_pad, 8);
+  static int32_t part_a_bytes(int32_t n_pieces) {
+    return (int32_t)sizeof(CtbBlobHeader) + pad(n_pieces * 4, 16);
   }
-  int32_t total_bytes(int32_t n_pieces, int32_t n_seg, int32_t n_ent_pad) const {
-    return n_pieces * CTB_PIECE * CTB_S * bytes_cd + meta_bytes(n_pieces, n_seg, n_ent_pad);
+  static int32_t part_b_bytes(int32_t n_seg, int32_t n_ent_pad) {
+    return n_seg * (int32_t)sizeof(CtbSeg) + 10 * pad(n_ent_pad, 8);
+  }
+  int32_t tile_bytes(int32_t n_pieces) const { return n_pieces * CTB_PIECE * CTB_S * bytes_cd; }
+  bool fits_counts(int32_t n_pieces, int32_t n_seg, int32_t n_ent_pad) const {
+    return tile_bytes(n_pieces) <= tile_cap && part_a_bytes(n_pieces) <= CTB_META_A_CAP &&
+           part_b_bytes(n_seg, n_ent_pad) <= meta_cap &&
+           n_pieces * CTB_PIECE <= 65532 && n_ent_pad <= 65532 * 4;
   }
   bool fits(int32_t extra_pieces, int32_t extra_ent) const {
-    return total_bytes((int32_t)cur_pieces.size() + extra_pieces, (int32_t)cur_segs.size() + 1,
-                       cur_ent_pad + pad(extra_ent, 4)) <= budget &&
-           ((int32_t)cur_pieces.size() + extra_pieces) * CTB_PIECE <= 65532;
+    return extra_ent <= 65535 &&
+           fits_counts((int32_t)cur_pieces.size() + extra_pieces, (int32_t)cur_segs.size() + 1,
+                       cur_ent_pad + pad(extra_ent, 4));
   }
   void add(Seg&& s) {
     cur_ent_pad += pad((int32_t)s.cols.size(), 4);
@@ -164,20 +169,30 @@ struct BundleBuilder {
     std::stable_sort(cur_segs.begin(), cur_segs.end(),
                      [](const Seg& a, const Seg& b) { return a.cols.size() > b.cols.size(); });
     const int32_t n_seg = (int32_t)cur_segs.size();
+    const int32_t n_p = (int32_t)cur_pieces.size();
     const int32_t n_ent_pad = pad(cur_ent_pad, 8);
-    CtbBlobHeader h{n_seg, n_ent_pad, (int32_t)sizeof(CtbBlobHeader) + n_seg * (int32_t)sizeof(CtbSeg), 0};
+    CtbBlobHeader h{};
+    h.n_pieces = n_p; h.n_seg = n_seg; h.n_ent_pad = n_ent_pad;
+    h.off_seg = 0;
+    h.off_w = n_seg * (int32_t)sizeof(CtbSeg);
     h.off_loc = h.off_w + 8 * n_ent_pad;
+    h.bytes_a = part_a_bytes(n_p);
+    h.bytes_b = pad(h.off_loc + 2 * n_ent_pad, 16);
     const size_t base = blob.size();
-    const size_t bytes = (size_t)pad(h.off_loc + 2 * n_ent_pad, 16);
+    const size_t bytes = (size_t)h.bytes_a + h.bytes_b;
     blob.resize(base + bytes, 0);
     std::memcpy(&blob[base], &h, sizeof h);
-    CtbSeg* segs = reinterpret_cast<CtbSeg*>(&blob[base + sizeof h]);
-    double* w = reinterpret_cast<double*>(&blob[base + h.off_w]);
-    uint16_t* loc = reinterpret_cast<uint16_t*>(&blob[base + h.off_loc]);
+    std::memcpy(&blob[base + sizeof h], cur_pieces.data(), (size_t)n_p * 4);
+    const size_t bb = base + h.bytes_a;
+    CtbSeg* segs = reinterpret_cast<CtbSeg*>(&blob[bb + h.off_seg]);
+    double* w = reinterpret_cast<double*>(&blob[bb + h.off_w]);
+    uint16_t* loc = reinterpret_cast<uint16_t*>(&blob[bb + h.off_loc]);
+    desc.push_back(make_int4((int)(base & 0xffffffffu), (int)(base >> 32), h.bytes_a, h.bytes_b));
     int32_t e = 0;
     for (int32_t i = 0; i < n_seg; ++i) {
       const Seg& s = cur_segs[i];
-      segs[i] = CtbSeg{s.target, e, (int32_t)s.cols.size(), 0};
+      segs[i] = CtbSeg{s.target, (uint16_t)(e / 4), (uint16_t)s.cols.size(),
+                       s.target >= 0 ? 1.0 / den[s.target] : 1.0};
       for (size_t k = 0; k < s.cols.size(); ++k) {
         const int32_t piece = s.cols[k] / CTB_PIECE;
         const int32_t lp = (int32_t)(std::lower_bound(cur_pieces.begin(), cur_pieces.end(), piece) -
@@ -187,12 +202,11 @@ struct BundleBuilder {
       }
       e += pad((int32_t)s.cols.size(), 4);
     }
-    pieces.insert(pieces.end(), cur_pieces.begin(), cur_pieces.end());
-    b_piece_ptr.push_back((int32_t)pieces.size());
     b_blob_off.push_back((int64_t)blob.size());
     n_segments += n_seg;
-    max_cells = std::max<int32_t>(max_cells, (int32_t)cur_pieces.size() * CTB_PIECE);
-    max_meta = std::max<int32_t>(max_meta, meta_bytes((int32_t)cur_pieces.size(), n_seg, n_ent_pad));
+    n_pieces_total += n_p;
+    max_cells = std::max<int32_t>(max_cells, n_p * CTB_PIECE);
+    max_meta = std::max<int32_t>(max_meta, h.bytes_b);
     cur_pieces.clear();
     cur_segs.clear();
     cur_ent_pad = 0;
@@ -215,7 +229,7 @@ extern "C" void ctb_plan_free(ctb_plan* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->d_row_cell); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_w);
-  cudaFree(p->d_den); cudaFree(p->d_b_piece_ptr); cudaFree(p->d_pieces); cudaFree(p->d_b_blob_off);
+  cudaFree(p->d_den); cudaFree(p->d_b_blob_off); cudaFree(p->d_b_desc); cudaFree(p->d_work_counter);
   cudaFree(p->d_blob); cudaFree(p->d_split_region); cudaFree(p->d_split_slot_ptr);
   cudaSetDevice(prev);
   delete p;
@@ -230,7 +244,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
                            int32_t* bad_axis) {
   const int64_t ncell = (int64_t)nlat_phys * nlon_phys;
   if (nlat <= 0 || nlon <= 0 || n_rows < 0 || R < 0 || nlat_phys < nlat || nlon_phys < nlon ||
-      ncell >= (1ll << 31) || n_rows >= (1ll << 31)) {
+      ncell >= (1ll << 30) || n_rows >= (1ll << 31)) {
     ctb_set_error("ctb_plan_build: invalid sizes (nlat=%d nlon=%d n_rows=%lld R=%d)", nlat, nlon,
                   (long long)n_rows, R);
     return CTB_ERR_INVALID;
@@ -384,12 +398,19 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
 
   // ---- staging bundles ----
   int32_t bytes_cd = opts && opts->stage_bytes_per_cell_day > 0 ? opts->stage_bytes_per_cell_day : 4;
-  int32_t budget = opts && opts->smem_budget_bytes > 0 ? opts->smem_budget_bytes : 74 * 1024;
+  // shared memory of one CTA = CTB_TILE_STAGES tiles + CTB_META_SLOTS metadata slots; a
+  // tile holds at most CTB_TILE_UNITS 16-byte units per day (register budget of the loads
+  // in flight).  smem_budget_bytes (tests) shrinks the tile to force region splitting.
+  const int32_t meta_cap = CTB_META_B_CAP;
+  int32_t tile_cap = CTB_TILE_BYTES;
+  if (opts && opts->smem_budget_bytes > 0) tile_cap = std::min(tile_cap, opts->smem_budget_bytes);
   BundleBuilder B;
   B.bytes_cd = bytes_cd;
-  B.budget = budget;
-  if (B.total_bytes(2, 1, 8) > budget) {
-    ctb_set_error("ctb_plan_build: smem budget %d too small", budget);
+  B.tile_cap = tile_cap;
+  B.meta_cap = meta_cap;
+  B.den = P->h_den.data();
+  if (!B.fits_counts(2, 1, 8)) {
+    ctb_set_error("ctb_plan_build: smem budget %d too small", tile_cap);
     return CTB_ERR_INVALID;
   }
 
@@ -485,7 +506,8 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
       const int32_t c = col[g.e0 + idx[q]];
       const int32_t p = c / CTB_PIECE;
       const int32_t np = fpieces + (p != last_piece ? 1 : 0);
-      if (!fc.empty() && B.total_bytes(np, 1, BundleBuilder::pad((int32_t)fc.size() + 1, 4)) > budget)
+      if (!fc.empty() && ((int32_t)fc.size() >= 65535 ||
+                          !B.fits_counts(np, 1, BundleBuilder::pad((int32_t)fc.size() + 1, 4))))
         flush();
       if (p != last_piece) { ++fpieces; last_piece = p; }
       fc.push_back(c);
@@ -511,22 +533,22 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   if ((rc = upload(&P->d_row_ptr, row_ptr))) return rc;
   if ((rc = upload(&P->d_col, col))) return rc;
   if ((rc = upload(&P->d_w, w))) return rc;
-  if ((rc = upload(&P->d_b_piece_ptr, B.b_piece_ptr))) return rc;
-  if ((rc = upload(&P->d_pieces, B.pieces))) return rc;
   if ((rc = upload(&P->d_b_blob_off, B.b_blob_off))) return rc;
   if ((rc = upload(&P->d_blob, B.blob))) return rc;
+  if ((rc = upload(&P->d_b_desc, B.desc))) return rc;
+  CTB_CUDA(cudaMalloc((void**)&P->d_work_counter, sizeof(int)));
   if ((rc = upload(&P->d_split_region, split_region))) return rc;
   if ((rc = upload(&P->d_split_slot_ptr, split_slot_ptr))) return rc;
-  P->n_bundles = (int32_t)B.b_piece_ptr.size() - 1;
+  P->n_bundles = (int32_t)B.b_blob_off.size() - 1;
   P->n_segments = B.n_segments;
   P->n_split = (int32_t)split_region.size();
   P->n_scratch = n_scratch;
 
   ctb_plan_info& I = P->info;
   I.n_rows = n_rows; I.nnz = P->nnz; I.n_cells_distinct = U; I.n_cells_grid = ncell;
-  I.n_regions = R; I.n_bundles = P->n_bundles; I.n_pieces = (int64_t)B.pieces.size();
+  I.n_regions = R; I.n_bundles = P->n_bundles; I.n_pieces = B.n_pieces_total;
   I.n_pieces_distinct = pieces_distinct; I.n_split_regions = P->n_split;
-  I.n_scratch_slots = n_scratch; I.cap_cells = budget / (CTB_S * bytes_cd); I.max_bundle_cells = B.max_cells;
+  I.n_scratch_slots = n_scratch; I.cap_cells = tile_cap / (CTB_S * bytes_cd); I.max_bundle_cells = B.max_cells;
   I.max_meta_bytes = B.max_meta;
   I.time_block = CTB_TB; I.max_region_rows = max_rows;
   CTB_CUDA(cudaDeviceSynchronize());

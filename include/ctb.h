@@ -162,6 +162,21 @@ int ctb_transform(const void* x0, const void* x1, int dtype, int64_t n, int tran
 int ctb_gather_rows(const ctb_plan* plan, const void* x, int dtype, int layout, int64_t stride,
                     const int32_t* time_index, int64_t T, void* out, void* stream);
 
+/* ---- diagnostics ---------------------------------------------------------- *
+ * Loads-only replay of the staging traffic of ctb_aggregate (TIME_MAJOR, f32) on the
+ * plan's real footprint; used by bench_micro/ to measure what the memory system delivers
+ * for a lane mapping (lanes_p pieces x 32/lanes_p days per warp), `unroll` loads in
+ * flight per thread, `warps` per CTA and `ctas_per_sm`.  `sink` is a 4-byte DEVICE word. */
+int ctb_debug_stage_bw(const ctb_plan* plan, const void* x, int64_t stride, int64_t T, int lanes_p,
+                       int unroll, int warps, int ctas_per_sm, void* sink, void* stream);
+/* Same traffic staged with cp.async copies of `width` bytes (4, 8, 16) straight into
+ * transposed shared-memory tiles, `nbuf` tile buffers in flight, `loader_warps` issuing. */
+/* Phase timers of the fused kernel (enabled by env CTB_DEBUG & 16): cycles of warp 0 summed
+ * over CTAs: {metadata, wait-gather, stage, wait-stage, gather, n_ctas, -, -}. */
+int ctb_debug_timers(unsigned long long* out8, int reset);
+int ctb_debug_cpasync_bw(const ctb_plan* plan, const void* x, int64_t stride, int64_t T, int width,
+                         int loader_warps, int nbuf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
