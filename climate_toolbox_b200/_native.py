@@ -23,7 +23,7 @@ SYMBOLS = (
     "ctb_version", "ctb_last_error", "ctb_launch_count", "ctb_plan_build", "ctb_plan_free",
     "ctb_plan_get_info", "ctb_plan_row_cells", "ctb_plan_den", "ctb_plan_row_weights",
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
-    "ctb_debug_stage_bw", "ctb_debug_cpasync_bw", "ctb_debug_timers",
+    "ctb_debug_stage_bw", "ctb_debug_cpasync_bw",
 )
 
 
@@ -89,8 +89,6 @@ def lib():
     L.ctb_debug_stage_bw.argtypes = [p, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.ctb_debug_cpasync_bw.restype = C.c_int
     L.ctb_debug_cpasync_bw.argtypes = [p, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp]
-    L.ctb_debug_timers.restype = C.c_int
-    L.ctb_debug_timers.argtypes = [C.POINTER(C.c_uint64), C.c_int]
     _lib = L
     return L
 

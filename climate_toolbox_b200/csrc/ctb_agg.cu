@@ -4,20 +4,25 @@
 // (sum(w*x)/sum(w) per region) with the transforms of
 // climate_toolbox/transformations/transformations.py:69-89,139-141,189 fused in.
 //
-// Fused kernel (TIME_MAJOR input [T][lat][lon], the BCSD layout): one CTA of 16 warps per
-// work item = one bundle (spatially adjacent regions whose gridcell footprint fits a
-// shared-memory tile) x one block of 32 days; two CTAs per SM, so one stages while the
-// other reduces (hardware barriers only -- no polling).
-//   metadata: the bundle's piece list, segment table, weights and staged-cell indices
-//           arrive as ONE bulk async copy (cp.async.bulk, TMA 1-D) signalled on an mbarrier;
+// Fused kernel (TIME_MAJOR input [T][lat][lon], the BCSD layout): CTAs of 16 warps, two per
+// SM, each looping over work units handed out by an atomic counter.  A work unit = one
+// bundle (spatially adjacent regions whose gridcell footprint fits a shared-memory tile) x a
+// chunk of 4 consecutive 32-day blocks, in chunk-major order so that CTAs running together
+// read neighbouring bundles of the same days (shared lines meet in L2).
+//   metadata: the bundle's piece list, segment table, weights and staged-cell indices arrive
+//           as ONE bulk async copy (cp.async.bulk, TMA 1-D) signalled on an mbarrier, once
+//           per unit;
 //   stage : 16-byte coalesced global loads of the footprint's 4-cell pieces for 32
-//           day-planes (8 in flight per thread, 32 warps per SM; shared memory is kept
-//           <= 164 KB per SM because the remaining L1 bounds the loads in flight,
-//           bench_micro/), written TRANSPOSED into smem as a
-//           cell-major tile sx[cell][day] (row stride 33 words => conflict-free both ways);
+//           day-planes, 8 in flight per thread, written TRANSPOSED into smem as a cell-major
+//           tile sx[cell][day] (row stride 33 words => conflict-free both ways); while a tile
+//           is staged the same footprint of the next block is prefetched into L2;
 //   gather: one warp per region, lane = day; per 4 CSR entries three vector LDS of
 //           metadata + four conflict-free LDS of data, fp64 FMA, NaN products skipped;
 //           out[r][t] = acc / den[r], 256-byte coalesced stores along time.
+// One CTA of an SM stages while the other gathers; only hardware barriers are used.
+// Shared memory is capped at 164 KB per SM: it is carved out of the L1, and the L1 that is
+// left bounds the loads in flight (bench_micro/stage_bw3.py: 4.2 -> 2.1 TB/s at 228 KB).
+// Alternatives that were built and measured slower are described in DESIGN.md.
 // Direct kernel (CELL_MAJOR input [lat][lon][T], or any layout as a fallback):
 //   one warp per (region, 32-day tile), lane = day, coalesced along time.
 #include <algorithm>
@@ -75,9 +80,6 @@ __device__ __forceinline__ double2 ld_stream_d2(const double* p) {
                : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
-
-// phase timers for CTB_DEBUG & 16 (perf experiments): sums of clock64 deltas of warp 0
-__device__ unsigned long long g_ctb_timers[8];
 
 // ---- mbarrier + bulk async copy (TMA 1-D; SASS: UBLKCP / SYNCS) ---------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -137,10 +139,11 @@ __device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TI
   }
 }
 
-template <typename TIN, int KIND, int NOUT, bool VEC>
-__global__ void __launch_bounds__(CTB_THREADS, CTB_CTAS_PER_SM)
+template <typename TIN, int KIND, int NOUT, bool VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
 agg_fused_kernel(const AggArgs a) {
   constexpr int NIN = NIn<KIND>::v;
+  constexpr int TILE_LOADS = 8;
   constexpr int S = CTB_S;
   constexpr int HALVES = sizeof(TIN) / 4;       // 16-byte units per piece-day of one input
   constexpr int CPU = 16 / sizeof(TIN);          // cells per unit
@@ -157,9 +160,6 @@ agg_fused_kernel(const AggArgs a) {
   // of the same days (shared lines meet in L2), and the bundle's metadata is fetched once
   // per unit.  While a tile is staged, the same footprint of the NEXT block is prefetched
   // into L2, so all but the first tile of a unit read L2-resident data.
-  long long tm[6] = {0, 0, 0, 0, 0, 0};
-  long long c0 = clock64();
-  auto lap = [&](int i) { const long long c1 = clock64(); tm[i] += c1 - c0; c0 = c1; };
   for (int n_done = 0;; ++n_done) {
   __syncthreads();   // previous unit fully reduced: tile, blob and s_unit may be reused
   if (tid == 0) {
@@ -176,7 +176,6 @@ agg_fused_kernel(const AggArgs a) {
   const int tb_begin = (unit / a.n_bundles) * a.chunk_tb;
   const int tb_end = min(tb_begin + a.chunk_tb, a.n_tb);
   mbar_wait(&s_bar, n_done & 1);
-  lap(0);   // unit fetch + metadata
   const CtbBlobHeader H = *reinterpret_cast<const CtbBlobHeader*>(s_blob);
   const int* s_piece = reinterpret_cast<const int*>(s_blob + sizeof(CtbBlobHeader));
   const unsigned char* mb = s_blob + H.bytes_a;
@@ -185,12 +184,11 @@ agg_fused_kernel(const AggArgs a) {
   for (int tb = tb_begin; tb < tb_end; ++tb) {
   const int t0 = tb * CTB_TB;
   if (tb != tb_begin) __syncthreads();   // tile buffer free again
-  lap(1);   // waiting for the other warps' gather
   // ---------------- stage: [day][piece] global  ->  [input][cell][day] shared -------------
   {
     const int l8 = lane & 7, l4 = lane >> 3;
     const int dl = (warp & 7) * 4 + l4;            // day within the tile
-    constexpr int NSUB = CTB_WARPS / 8;            // warps sharing one 4-day group
+    constexpr int NSUB = (THREADS / 32) / 8;            // warps sharing one 4-day group
     const int sub = warp >> 3;
     const int t = t0 + dl;
     const int n_units = nP * HALVES * NIN;         // unit index: [input][piece][half]
@@ -203,11 +201,11 @@ agg_fused_kernel(const AggArgs a) {
       const bool pf = tn < a.T && tb + 1 < tb_end && !(a.dbg & 8);
       const int64_t pf_delta = pf ? ((a.tix ? (int64_t)a.tix[tn] : (int64_t)tn) - tp) * a.stride : 0;
       TIN* sx = reinterpret_cast<TIN*>(smem_raw) + dl;
-      for (int g0 = l8 + 8 * sub; g0 < n_units; g0 += 8 * NSUB * CTB_LOADS) {
-        int off[CTB_LOADS];
-        uint32_t v[CTB_LOADS][4];
+      for (int g0 = l8 + 8 * sub; g0 < n_units; g0 += 8 * NSUB * TILE_LOADS) {
+        int off[TILE_LOADS];
+        uint32_t v[TILE_LOADS][4];
 #pragma unroll
-        for (int u = 0; u < CTB_LOADS; ++u) {      // all index reads first, then all loads
+        for (int u = 0; u < TILE_LOADS; ++u) {      // all index reads first, then all loads
           const int g = g0 + 8 * NSUB * u;
           off[u] = -1;
           if (g < n_units) {
@@ -216,7 +214,7 @@ agg_fused_kernel(const AggArgs a) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < CTB_LOADS; ++u) {
+        for (int u = 0; u < TILE_LOADS; ++u) {
           if (off[u] >= 0) {
             const int o = off[u] & ~(1 << 30);
             const TIN* src = (NIN == 2 && (off[u] >> 30)) ? p1 + o : p0 + o;
@@ -242,7 +240,7 @@ agg_fused_kernel(const AggArgs a) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < CTB_LOADS; ++u) {
+        for (int u = 0; u < TILE_LOADS; ++u) {
           const int g = g0 + 8 * NSUB * u;
           if (off[u] >= 0 && !(a.dbg & 2)) {
             // unit g covers cells [g*CPU, g*CPU + CPU) of the [input][cell] row space
@@ -260,9 +258,7 @@ agg_fused_kernel(const AggArgs a) {
       }
     }
   }
-  lap(2);   // own staging (loads + transposed stores)
   __syncthreads();
-  lap(3);   // waiting for the other warps' staging
 
   // ---------------- gather + segmented weighted sum: warp = region, lane = day ------------
   const CtbSeg* segs = reinterpret_cast<const CtbSeg*>(mb + H.off_seg);
@@ -272,7 +268,7 @@ agg_fused_kernel(const AggArgs a) {
   const TIN* sx1 = sx0 + (size_t)nP * CTB_PIECE * S;
   const int t = t0 + lane;
   // segments are sorted longest-first: round-robin over the warps is balanced
-  for (int s = warp; s < ((a.dbg & 4) ? 0 : H.n_seg); s += CTB_WARPS) {
+  for (int s = warp; s < ((a.dbg & 4) ? 0 : H.n_seg); s += (THREADS / 32)) {
     const CtbSeg sg = segs[s];
     double acc[NOUT], acc2[NOUT];
 #pragma unroll
@@ -316,13 +312,8 @@ agg_fused_kernel(const AggArgs a) {
       }
     }
   }
-  lap(4);   // own gather
   }   // tiles of the unit
   }   // units
-  if ((a.dbg & 16) && warp == 0 && lane == 0) {
-    for (int i = 0; i < 5; ++i) atomicAdd(&g_ctb_timers[i], (unsigned long long)tm[i]);
-    atomicAdd(&g_ctb_timers[5], 1ull);
-  }
 }
 
 // Regions split over several bundles (and regions with no kept rows):
@@ -380,43 +371,40 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(const AggArgs a) {
 }
 
 // ------------------------------------------------------------- dispatch -----
-template <typename TIN, int KIND, int NOUT>
+template <typename TIN, int KIND, int NOUT, int THREADS>
 int launch_staged(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
   constexpr int NIN = NIn<KIND>::v;
   const size_t tile = ((size_t)NIN * P->info.max_bundle_cells * CTB_S * sizeof(TIN) + 127) & ~(size_t)127;
   const size_t meta = (size_t)CTB_META_A_CAP + (((size_t)P->info.max_meta_bytes + 15) & ~(size_t)15);
   const size_t smem = tile + meta;
-  int dev_max = 0;
-  CTB_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
-  const size_t units = (size_t)NIN * (P->info.max_bundle_cells / CTB_PIECE) * (sizeof(TIN) / 4);
-  if (smem > (size_t)dev_max) {
-    ctb_set_error("staging tile (%zu bytes, %zu units) exceeds the kernel limits: rebuild the plan "
-                  "with stage_bytes_per_cell_day=%d", smem, units, (int)(NIN * sizeof(TIN)));
-    return CTB_ERR_UNSUPPORTED;
-  }
+  int n_sm = 0;
+  CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
+  const int by_smem = (int)((164 * 1024) / (smem + 1024 + 64));
+  const int ctas_per_sm = std::max(1, std::min(2, by_smem));
   const int n_tb = (a.T + CTB_TB - 1) / CTB_TB;
-  int chunk_tb = 8;
+  int chunk_tb = 4;
   if (const char* e = getenv("CTB_CHUNK_TB")) chunk_tb = std::max(1, atoi(e));
   const int n_chunks = (n_tb + chunk_tb - 1) / std::max(chunk_tb, 1);
-  chunk_tb = n_chunks ? (n_tb + n_chunks - 1) / n_chunks : 1;   // even chunks
+  chunk_tb = n_chunks ? (n_tb + n_chunks - 1) / n_chunks : 1;
   const int64_t n_units = (int64_t)P->n_bundles * n_chunks;
   if (n_units >= (1ll << 31)) { ctb_set_error("too many work units"); return CTB_ERR_UNSUPPORTED; }
   a.n_bundles = P->n_bundles; a.n_items = (int)n_units; a.n_tb = n_tb; a.chunk_tb = std::max(chunk_tb, 1);
   a.tile_stride = (int)tile; a.meta_b_stride = 0; a.work_counter = P->d_work_counter;
   { const char* e = getenv("CTB_DEBUG"); a.dbg = e ? atoi(e) : 0; }
   if (n_units > 0) {
-    int n_sm = 0;
-    CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
-    const unsigned grid = (unsigned)std::min<int64_t>(n_units, (int64_t)n_sm * CTB_CTAS_PER_SM);
+    const unsigned grid = (unsigned)std::min<int64_t>(n_units, (int64_t)n_sm * ctas_per_sm);
+    const int carveout = (int)((ctas_per_sm * (smem + 1024 + 64) + 2048) * 100 / (228 * 1024)) + 1;
     CTB_CUDA(cudaMemsetAsync(P->d_work_counter, 0, sizeof(int), st));
     if (vec) {
-      auto k = agg_fused_kernel<TIN, KIND, NOUT, true>;
+      auto k = agg_fused_kernel<TIN, KIND, NOUT, true, THREADS>;
       CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, CTB_THREADS, smem, st>>>(a);
+      CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(carveout, 100)));
+      k<<<grid, THREADS, smem, st>>>(a);
     } else {
-      auto k = agg_fused_kernel<TIN, KIND, NOUT, false>;
+      auto k = agg_fused_kernel<TIN, KIND, NOUT, false, THREADS>;
       CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, CTB_THREADS, smem, st>>>(a);
+      CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(carveout, 100)));
+      k<<<grid, THREADS, smem, st>>>(a);
     }
     CTB_LAUNCH_CHECK();
   }
@@ -444,7 +432,10 @@ int launch_direct(const ctb_plan* P, const AggArgs& a, int layout, cudaStream_t 
 
 template <typename TIN, int KIND, int NOUT>
 int run(const ctb_plan* P, const AggArgs& a, int layout, int variant, bool vec, cudaStream_t st) {
-  if (variant == 1) return launch_staged<TIN, KIND, NOUT>(P, a, vec, st);
+  // 16 warps per CTA for the plain aggregation (64 registers suffice); the transform
+  // variants take 8 warps with up to 128 registers (no spills in the fp64 EDD/poly code)
+  constexpr int THREADS = (KIND == CTB_TR_IDENTITY) ? 512 : 256;
+  if (variant == 1) return launch_staged<TIN, KIND, NOUT, THREADS>(P, a, vec, st);
   return launch_direct<TIN, KIND, NOUT>(P, a, layout, st);
 }
 
@@ -536,9 +527,9 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
   if (rc) return rc;
   if (ctb_tr_nin(transform) == 2 && !x1) { ctb_set_error("transform needs two inputs"); return CTB_ERR_INVALID; }
   if (variant == 0) variant = (layout == CTB_LAYOUT_TIME_MAJOR) ? 1 : 2;
-  if (variant == 1 && layout != CTB_LAYOUT_TIME_MAJOR) { ctb_set_error("staged variant needs TIME_MAJOR input"); return CTB_ERR_INVALID; }
+  if (variant != 2 && layout != CTB_LAYOUT_TIME_MAJOR) { ctb_set_error("staged variant needs TIME_MAJOR input"); return CTB_ERR_INVALID; }
   if (variant != 1 && variant != 2) { ctb_set_error("variant=%d unsupported", variant); return CTB_ERR_INVALID; }
-  const size_t need = variant == 1 ? ctb_aggregate_workspace_bytes(P, T, n_out) : 0;
+  const size_t need = variant != 2 ? ctb_aggregate_workspace_bytes(P, T, n_out) : 0;
   if (need > 0 && (!workspace || workspace_bytes < need)) {
     ctb_set_error("workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
     return CTB_ERR_INVALID;
@@ -573,12 +564,21 @@ template <int UNR>
 __global__ void debug_stage_bw_kernel(const float* __restrict__ x, int64_t stride, int T,
                                       const int64_t* __restrict__ b_blob_off,
                                       const unsigned char* __restrict__ blob, int n_bundles,
-                                      int n_items, int lanes_p, float* sink, int pf_blocks) {
+                                      int n_items, int lanes_p, float* sink, int pf_blocks, int order_chunk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int lp = lane % lanes_p, ld = lane / lanes_p, dpw = 32 / lanes_p, ndg = 32 / dpw;
   float acc = 0.f;
-  for (int64_t idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-    const int b = (int)(idx % n_bundles), t0 = (int)(idx / n_bundles) * CTB_TB;
+  for (int64_t idx0 = blockIdx.x; idx0 < n_items; idx0 += gridDim.x) {
+    int b = (int)(idx0 % n_bundles), t0 = (int)(idx0 / n_bundles) * CTB_TB;
+    if (order_chunk > 0) {
+      // unit-major order: a CTA keeps one bundle for `order_chunk` consecutive time blocks
+      const int n_tb = n_items / n_bundles, n_ch = (n_tb + order_chunk - 1) / order_chunk;
+      const int64_t k = idx0 / gridDim.x;                    // CTA-local item number
+      const int64_t unit = blockIdx.x + (k / order_chunk) * gridDim.x;
+      const int tb = (int)(unit / n_bundles) * order_chunk + (int)(k % order_chunk);
+      if (unit >= (int64_t)n_bundles * n_ch || tb >= n_tb) continue;
+      b = (int)(unit % n_bundles); t0 = tb * CTB_TB;
+    }
     const unsigned char* bl = blob + b_blob_off[b];
     const int nP = reinterpret_cast<const CtbBlobHeader*>(bl)->n_pieces;
     const int* pieces = reinterpret_cast<const int*>(bl + sizeof(CtbBlobHeader));
@@ -631,7 +631,9 @@ extern "C" int ctb_debug_stage_bw(const ctb_plan* P, const void* x, int64_t stri
   int pf_blocks = 0;
   if (const char* e = getenv("CTB_DBG_SMEM")) dsm = (size_t)atoi(e);
   if (const char* e = getenv("CTB_DBG_PF")) pf_blocks = atoi(e);
-#define CTB_DBG(U) if (dsm) CTB_CUDA(cudaFuncSetAttribute(debug_stage_bw_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); debug_stage_bw_kernel<U><<<grid, warps * 32, dsm, st>>>((const float*)x, stride, (int)T, P->d_b_blob_off, P->d_blob, P->n_bundles, (int)n_items, lanes_p, (float*)sink, pf_blocks)
+  int order_chunk = 0;
+  if (const char* e = getenv("CTB_DBG_ORDER")) order_chunk = atoi(e);
+#define CTB_DBG(U) if (dsm) CTB_CUDA(cudaFuncSetAttribute(debug_stage_bw_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); debug_stage_bw_kernel<U><<<grid, warps * 32, dsm, st>>>((const float*)x, stride, (int)T, P->d_b_blob_off, P->d_blob, P->n_bundles, (int)n_items, lanes_p, (float*)sink, pf_blocks, order_chunk)
   switch (unroll) {
     case 2: CTB_DBG(2); break;
     case 4: CTB_DBG(4); break;
@@ -730,14 +732,5 @@ extern "C" int ctb_debug_cpasync_bw(const ctb_plan* P, const void* x, int64_t st
   else { ctb_set_error("width must be 4, 8 or 16"); return CTB_ERR_INVALID; }
 #undef CTB_CPA
   CTB_LAUNCH_CHECK();
-  return CTB_OK;
-}
-
-extern "C" int ctb_debug_timers(unsigned long long* out8, int reset) {
-  if (out8) CTB_CUDA(cudaMemcpyFromSymbol(out8, g_ctb_timers, sizeof(unsigned long long) * 8));
-  if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CTB_CUDA(cudaMemcpyToSymbol(g_ctb_timers, z, sizeof z));
-  }
   return CTB_OK;
 }

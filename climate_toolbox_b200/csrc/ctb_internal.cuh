@@ -58,16 +58,13 @@ struct CtbSeg {
 };
 static_assert(sizeof(CtbBlobHeader) == 32 && sizeof(CtbSeg) == 16, "blob layout");
 
-// fused kernel geometry: CTAs of 16 warps, two per SM.  Every thread stages CTB_LOADS
-// 16-byte loads per tile, so a tile holds CTB_THREADS * CTB_LOADS / 32 = 128 16-byte units
-// per day.  Shared memory is deliberately limited to 164 KB per SM: it is carved out of the
-// L1, and the L1 capacity that is left bounds the loads in flight -- measured
-// (bench_micro/stage_bw3.py): 4.2 TB/s of staging traffic with <= 82 KB per CTA, 2.9 TB/s
-// with 98 KB, 2.1 TB/s with 115 KB.
-constexpr int CTB_THREADS = 512;
-constexpr int CTB_WARPS = CTB_THREADS / 32;
-constexpr int CTB_LOADS = 8;                                      // loads in flight per thread
-constexpr int CTB_TILE_UNITS = CTB_THREADS * CTB_LOADS / CTB_TB;  // 128
+// fused kernel geometry: CTAs of up to 16 warps, two per SM; every thread stages 8 16-byte
+// loads per batch, so a 16-warp CTA fills a 128-unit tile in one batch.
+// Shared memory is deliberately limited to 164 KB per SM (82 KB per CTA): it is carved out
+// of the L1, and the L1 that is left bounds the loads in flight -- measured
+// (bench_micro/stage_bw3.py): 4.2 TB/s of staging traffic with <= 164 KB/SM, 2.9 TB/s with
+// 196 KB, 2.1 TB/s with 228 KB.
+constexpr int CTB_TILE_UNITS = 128;                               // 16-byte units per day in a tile
 constexpr int CTB_TILE_BYTES = CTB_TILE_UNITS * 4 * CTB_S * 4;    // 67,584 B of shared memory
 constexpr int CTB_CTAS_PER_SM = 2;
 constexpr int CTB_SMEM_PER_CTA = 164 * 1024 / CTB_CTAS_PER_SM - 1024 - 512;  // 82,432 B

@@ -171,9 +171,6 @@ int ctb_debug_stage_bw(const ctb_plan* plan, const void* x, int64_t stride, int6
                        int unroll, int warps, int ctas_per_sm, void* sink, void* stream);
 /* Same traffic staged with cp.async copies of `width` bytes (4, 8, 16) straight into
  * transposed shared-memory tiles, `nbuf` tile buffers in flight, `loader_warps` issuing. */
-/* Phase timers of the fused kernel (enabled by env CTB_DEBUG & 16): cycles of warp 0 summed
- * over CTAs: {metadata, wait-gather, stage, wait-stage, gather, n_ctas, -, -}. */
-int ctb_debug_timers(unsigned long long* out8, int reset);
 int ctb_debug_cpasync_bw(const ctb_plan* plan, const void* x, int64_t stride, int64_t T, int width,
                          int loader_warps, int nbuf, void* stream);
 
