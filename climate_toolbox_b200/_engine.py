@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -184,6 +185,30 @@ def _stream_ptr(device, stream=None):
     return C.c_void_p(s.cuda_stream)
 
 
+def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out, variant, out, out_ld,
+            workspace, stream):
+    """Raw-pointer call of ctb_aggregate (p0/p1: device or mapped-host addresses)."""
+    dev = plan.device
+    L = N.lib()
+    if out is None:
+        out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
+    ws_bytes = L.ctb_aggregate_workspace_bytes(plan._h, T, n_out) \
+        if (variant & 0xff) != N.VARIANT_DIRECT and layout == N.LAYOUT_TIME_MAJOR else 0
+    if ws_bytes and (workspace is None or workspace.numel() * 8 < ws_bytes):
+        workspace = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
+    tix_d = plan.time_index_device(tix)
+    pa, pp = _params_array(kind, params)
+    rc = L.ctb_aggregate(
+        plan._h, C.c_void_p(p0), C.c_void_p(p1) if p1 else None, ctb_dtype, layout, int(stride),
+        C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
+        _KIND[kind], pp, int(pa.size), int(n_out), C.c_void_p(out.data_ptr()), int(out_ld),
+        C.c_void_p(workspace.data_ptr()) if workspace is not None else None,
+        int(workspace.numel() * 8) if workspace is not None else 0, int(variant),
+        _stream_ptr(dev, stream))
+    N.check(rc)
+    return out
+
+
 def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", params=(), n_out=1,
                      variant=N.VARIANT_AUTO, out=None, out_ld=0, stream=None, workspace=None):
     """Launch the fused kernel on device-resident inputs.
@@ -198,40 +223,42 @@ def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", para
         raise TypeError("unsupported dtype {}".format(x0.dtype))
     if x1 is not None and (x1.dtype != x0.dtype or x1.shape != x0.shape):
         raise ValueError("the two inputs must agree in dtype and shape")
-    if out is None:
-        out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
-    L = N.lib()
-    ws_bytes = L.ctb_aggregate_workspace_bytes(plan._h, T, n_out) \
-        if variant != N.VARIANT_DIRECT and layout == N.LAYOUT_TIME_MAJOR else 0
-    if ws_bytes and (workspace is None or workspace.numel() * 8 < ws_bytes):
-        workspace = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
-    tix_d = plan.time_index_device(tix)
-    pa, pp = _params_array(kind, params)
-    rc = L.ctb_aggregate(
-        plan._h, C.c_void_p(x0.data_ptr()), C.c_void_p(x1.data_ptr()) if x1 is not None else None,
-        _T2CTB[x0.dtype], layout, int(stride),
-        C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
-        _KIND[kind], pp, int(pa.size), int(n_out), C.c_void_p(out.data_ptr()), int(out_ld),
-        C.c_void_p(workspace.data_ptr()) if workspace is not None else None,
-        int(workspace.numel() * 8) if workspace is not None else 0, int(variant),
-        _stream_ptr(dev, stream))
-    N.check(rc)
-    return out
+    return _launch(plan, x0.data_ptr(), x1.data_ptr() if x1 is not None else 0, _T2CTB[x0.dtype], layout,
+                   stride, tix, T, kind, params, n_out, variant, out, out_ld, workspace, stream)
+
+
+def _all_pinned(xs):
+    try:
+        return all(torch.from_numpy(x).is_pinned() for x in xs)
+    except Exception:
+        return False
 
 
 def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(), n_out=1,
-                   variant=N.VARIANT_AUTO, chunk_bytes=256 << 20):
+                   variant=N.VARIANT_AUTO, chunk_bytes=256 << 20, zero_copy=None):
     """Host (numpy) inputs: time-chunked H2D copies double-buffered against the kernel.
 
     ``xs``: list of 1 or 2 C-contiguous numpy arrays viewed as 2-D
-    (TIME_MAJOR: [t_phys, stride]; CELL_MAJOR: [ncell, stride]).  Pinned arrays copy
-    asynchronously at PCIe speed; pageable ones go through the driver's staging.
+    (TIME_MAJOR: [t_phys, stride]; CELL_MAJOR: [ncell, stride]).  Pinned TIME_MAJOR arrays
+    are read in place by the kernel (zero-copy); otherwise time chunks are copied (pinned:
+    asynchronously at PCIe speed; pageable: through the driver's staging).
     Returns a CUDA tensor [n_out, R, T].
     """
     dev = plan.device
     out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
     if T == 0 or plan.R == 0:
         return out
+    if zero_copy is None:
+        # opt-in: on the round-1 box the in-place read moved 2.5 GB at ~7 GB/s (16-byte requests
+        # over PCIe) and lost to copying all 6 GB at ~21 GB/s (profiles/r1_e2e_notes.md)
+        zero_copy = os.environ.get("CTB_ZERO_COPY", "0") == "1"
+    if zero_copy and layout == N.LAYOUT_TIME_MAJOR and (variant & 0xff) != N.VARIANT_DIRECT \
+            and xs[0].dtype in _NP2CTB and _all_pinned(xs):
+        # pinned (mapped) host arrays: the kernel reads them in place over PCIe, so only the
+        # referenced gridcells (~30 % of a global land/ocean grid) cross the bus
+        return _launch(plan, xs[0].ctypes.data, xs[1].ctypes.data if len(xs) > 1 else 0,
+                       _NP2CTB[xs[0].dtype], layout, stride, tix, T, kind, params, n_out,
+                       N.VARIANT_STAGED | 0x100, out, 0, None, None)
     ts = [torch.from_numpy(x) for x in xs]
     if layout == N.LAYOUT_CELL_MAJOR:
         d = [t.to(dev, non_blocking=True) for t in ts]

@@ -56,6 +56,7 @@ struct AggArgs {
   int n_tb;         // time blocks: ceil(T / 32)
   int chunk_tb;     // time blocks per work unit (a CTA keeps one bundle for a whole unit)
   int* work_counter; // device counter for dynamic unit scheduling (zeroed per launch)
+  int no_prefetch;  // inputs live in mapped host memory: no L2 prefetch
   int dbg;          // CTB_DEBUG bits (perf experiments): 1 skip loads, 2 skip STS, 4 skip gather
   const int32_t *row_ptr, *col;
   const double* w;
@@ -198,7 +199,7 @@ agg_fused_kernel(const AggArgs a) {
       const TIN* p1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) + tp * a.stride : p0;
       // the same footprint one time block later: prefetched into L2 now, staged next iteration
       const int tn = t + CTB_TB;
-      const bool pf = tn < a.T && tb + 1 < tb_end && !(a.dbg & 8);
+      const bool pf = tn < a.T && tb + 1 < tb_end && !a.no_prefetch && !(a.dbg & 8);
       const int64_t pf_delta = pf ? ((a.tix ? (int64_t)a.tix[tn] : (int64_t)tn) - tp) * a.stride : 0;
       TIN* sx = reinterpret_cast<TIN*>(smem_raw) + dl;
       for (int g0 = l8 + 8 * sub; g0 < n_units; g0 += 8 * NSUB * TILE_LOADS) {
@@ -526,6 +527,9 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
   int rc = ctb_pack_transform(transform, params, n_params, n_out, &a.tr);
   if (rc) return rc;
   if (ctb_tr_nin(transform) == 2 && !x1) { ctb_set_error("transform needs two inputs"); return CTB_ERR_INVALID; }
+  // bit 8 of `variant`: do not prefetch the next block into L2 (inputs in mapped host memory)
+  const bool no_prefetch = (variant & 0x100) != 0;
+  variant &= 0xff;
   if (variant == 0) variant = (layout == CTB_LAYOUT_TIME_MAJOR) ? 1 : 2;
   if (variant != 2 && layout != CTB_LAYOUT_TIME_MAJOR) { ctb_set_error("staged variant needs TIME_MAJOR input"); return CTB_ERR_INVALID; }
   if (variant != 1 && variant != 2) { ctb_set_error("variant=%d unsupported", variant); return CTB_ERR_INVALID; }
@@ -545,6 +549,7 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
   a.b_blob_off = P->d_b_blob_off; a.blob = P->d_blob; a.b_desc = P->d_b_desc; a.row_ptr = P->d_row_ptr; a.col = P->d_col;
   a.w = P->d_w; a.split_region = P->d_split_region; a.split_slot_ptr = P->d_split_slot_ptr;
   a.n_split = P->n_split;
+  a.no_prefetch = no_prefetch ? 1 : 0;
   const size_t es = dtype == CTB_F32 ? 4 : 8;
   const bool vec = (P->ncell % CTB_PIECE == 0) && ((stride * es) % 16 == 0) &&
                    ((uintptr_t)x0 % 16 == 0) && (!x1 || (uintptr_t)x1 % 16 == 0);

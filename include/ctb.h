@@ -144,7 +144,9 @@ int ctb_plan_row_weights(const ctb_plan* plan, double* w_out /*[n_rows]*/);
  *                  A time-chunked caller passes out + t0 with out_ld = total T.
  *  workspace     : DEVICE scratch of ctb_aggregate_workspace_bytes() bytes (may be
  *                  NULL when that is 0)
- *  variant       : 0 = auto; 1 = staged (TIME_MAJOR only); 2 = direct warp-per-region
+ *  variant       : 0 = auto; 1 = fused staged kernel (TIME_MAJOR only); 2 = direct
+ *                  warp-per-region kernel.  | 0x100: x0/x1 are MAPPED PINNED HOST memory read
+ *                  in place over PCIe (zero-copy: only the referenced gridcells cross the bus)
  */
 size_t ctb_aggregate_workspace_bytes(const ctb_plan* plan, int64_t T, int n_out);
 int ctb_aggregate(const ctb_plan* plan, const void* x0, const void* x1, int dtype, int layout,

@@ -173,6 +173,28 @@ def test_config1_shape_areawt(where, variant):
     check(out.tas.values, ref, scale)
 
 
+@pytest.mark.parametrize("mode", ["zero_copy_pinned", "chunked_pinned", "chunked_pageable"])
+def test_host_input_paths(mode):
+    """Host arrays: pinned memory is read in place by the kernel (zero-copy over PCIe); the
+    fallback copies time chunks double-buffered against the kernel.  70 days with a 1 MB chunk
+    budget forces several chunks and a ragged last one."""
+    lat, lon, df, tas, _, _ = _config(1.0, 3000, 70)
+    if mode != "chunked_pageable":
+        host = torch.empty(tas.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(torch.from_numpy(tas))
+        arr = host.numpy()
+    else:
+        arr = tas
+    grid = E.GridSpec(lat, lon)
+    plan = E.get_plan(grid, df, "areawt", "hierid")
+    n0 = E.launch_count()
+    out = E.aggregate_host(plan, [arr.reshape(70, -1)], N.LAYOUT_TIME_MAJOR, arr.shape[1] * arr.shape[2],
+                           None, 70, chunk_bytes=1 << 20, zero_copy=(mode == "zero_copy_pinned"))
+    assert (E.launch_count() - n0 == 1) == (mode == "zero_copy_pinned")
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "areawt", "hierid")
+    check(out[0].cpu().numpy().T, ref, scale)
+
+
 @pytest.mark.parametrize("aggwt,agglev", [("popwt", "hierid"), ("cropwt", "hierid"), ("popwt", "ISO")])
 def test_quarter_degree_sample_vs_oracle(aggwt, agglev):
     """Full 0.25-degree grid and 24,378 regions, a few days (oracle finishes in seconds).
