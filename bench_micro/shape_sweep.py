@@ -1,4 +1,8 @@
-"""Sweep CTA shapes of the per-unit CTA kernel (variants 3/4) against the warp-specialised one (variant 1)."""
+"""Sweep tile size (plan smem budget) and chunk length of the fused kernel.
+
+The round-1 sweep (profiles/micro/r1_sweep1.log) also compared CTA shapes: 256- vs 512-thread
+per-unit CTAs ("variant 3/4") and the warp-specialised persistent kernel ("variant 1" then);
+the 512-thread per-unit CTA won and is what ctb_aggregate runs now."""
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,10 +19,8 @@ for budget in (67584, 50688, 44352, 38016, 31680, 25344):
     plan = E.get_plan(E.GridSpec(lat, lon), df, "popwt", "hierid", smem_budget=budget, cache=False)
     out = torch.empty((1, plan.R, T), dtype=torch.float64, device=dev)
     i = plan.info
-    for variant in (3, 4, 1):
-        if variant == 1 and budget != 67584:
-            continue
-        for chunk in ((8,) if variant == 1 else (4, 8, 16)):
+    for variant in (1,):
+        for chunk in (2, 4, 8, 16):
             os.environ["CTB_CHUNK_TB"] = str(chunk)
             try:
                 for _ in range(3):
