@@ -123,6 +123,7 @@ class Plan:
 
 _PLAN_CACHE: "OrderedDict[str, Plan]" = OrderedDict()
 _PLAN_CACHE_SIZE = 8
+_PLAN_FAST = {}   # fingerprint of (DataFrame object, columns, grid) -> content key
 
 
 def region_codes(labels):
@@ -139,6 +140,24 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     for col in ("lat", "lon", agglev, aggwt, backup_aggwt):
         if col not in weights:
             raise KeyError(col)
+    # fast path: the same DataFrame object asked for again (the reference memoises its weights
+    # frame per path, aggregations.py:127).  Guarded by cheap fingerprints of the columns used,
+    # so an in-place edit of the frame still rebuilds the plan.
+    fp = None
+    if cache:
+        gh = hashlib.sha1()
+        grid.digest(gh)
+        with np.errstate(all="ignore"):
+            fp = (id(weights), len(weights), aggwt, agglev, backup_aggwt, stage_bytes, smem_budget,
+                  str(device), gh.hexdigest(),
+                  tuple(float(np.nansum(np.asarray(weights[c].values, dtype=np.float64)))
+                        for c in ("lat", "lon", aggwt, backup_aggwt)),
+                  str(weights[agglev].values[0]) if len(weights) else "",
+                  str(weights[agglev].values[-1]) if len(weights) else "")
+        hit = _PLAN_FAST.get(fp)
+        if hit is not None and hit in _PLAN_CACHE:
+            _PLAN_CACHE.move_to_end(hit)
+            return _PLAN_CACHE[hit]
     row_lat = np.ascontiguousarray(weights["lat"].values, dtype=np.float64)
     row_lon = np.ascontiguousarray(weights["lon"].values, dtype=np.float64)
     wp = np.ascontiguousarray(weights[aggwt].values, dtype=np.float64)
@@ -154,6 +173,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     key = h.hexdigest()
     if cache and key in _PLAN_CACHE:
         _PLAN_CACHE.move_to_end(key)
+        _PLAN_FAST[fp] = key
         return _PLAN_CACHE[key]
 
     opts = N.PlanOpts()
@@ -170,8 +190,12 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     plan = Plan(handle, device, labels, len(row_lat))
     if cache:
         _PLAN_CACHE[key] = plan
+        _PLAN_FAST[fp] = key
         while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
             _PLAN_CACHE.popitem(last=False)
+        if len(_PLAN_FAST) > 4 * _PLAN_CACHE_SIZE:
+            for k in [k for k, v in _PLAN_FAST.items() if v not in _PLAN_CACHE]:
+                del _PLAN_FAST[k]
     return plan
 
 
