@@ -77,6 +77,7 @@ class Plan:
         self._tix_cache = {}
 
     R = property(lambda s: s.info["n_regions"])
+    compact = property(lambda s: s.info["n_packed_cells"] > 0)
 
     def _host_array(self, fn, n, dtype, ptr):
         out = np.empty(n, dtype=dtype)
@@ -134,7 +135,7 @@ def region_codes(labels):
 
 
 def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4, device=None,
-             smem_budget=0, cache=True):
+             smem_budget=0, cache=True, compact=False):
     """Build (or fetch) the device plan for (grid, weights[lat, lon, agglev, aggwt, backup])."""
     device = device or default_device()
     for col in ("lat", "lon", agglev, aggwt, backup_aggwt):
@@ -149,7 +150,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
         grid.digest(gh)
         with np.errstate(all="ignore"):
             fp = (id(weights), len(weights), aggwt, agglev, backup_aggwt, stage_bytes, smem_budget,
-                  str(device), gh.hexdigest(),
+                  bool(compact), str(device), gh.hexdigest(),
                   tuple(float(np.nansum(np.asarray(weights[c].values, dtype=np.float64)))
                         for c in ("lat", "lon", aggwt, backup_aggwt)),
                   str(weights[agglev].values[0]) if len(weights) else "",
@@ -169,7 +170,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     grid.digest(h)
     for a in (row_lat, row_lon, wp, wb, codes):
         h.update(a.tobytes())
-    h.update(repr((stage_bytes, smem_budget, str(device), len(labels))).encode())
+    h.update(repr((stage_bytes, smem_budget, bool(compact), str(device), len(labels))).encode())
     key = h.hexdigest()
     if cache and key in _PLAN_CACHE:
         _PLAN_CACHE.move_to_end(key)
@@ -179,6 +180,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     opts = N.PlanOpts()
     opts.stage_bytes_per_cell_day = int(stage_bytes)
     opts.smem_budget_bytes = int(smem_budget)
+    opts.compact = 1 if compact else 0
     handle = C.c_void_p()
     bad_row, bad_axis = C.c_int64(-1), C.c_int32(-1)
     rc = N.lib().ctb_plan_build(
@@ -258,75 +260,107 @@ def _all_pinned(xs):
         return False
 
 
+_PINNED = {}   # (slot, k) -> pinned staging tensor for packed chunks (reused across calls)
+
+
+def _pinned_buffer(key, nbytes):
+    b = _PINNED.get(key)
+    if b is None or b.numel() < nbytes:
+        b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        _PINNED[key] = b
+    return b
+
+
 def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(), n_out=1,
-                   variant=N.VARIANT_AUTO, chunk_bytes=256 << 20, zero_copy=None):
-    """Host (numpy) inputs: time-chunked H2D copies double-buffered against the kernel.
+                   variant=N.VARIANT_AUTO, chunk_bytes=96 << 20, zero_copy=None, threads=0):
+    """Host (numpy) inputs -> CUDA tensor [n_out, R, T].
 
     ``xs``: list of 1 or 2 C-contiguous numpy arrays viewed as 2-D
-    (TIME_MAJOR: [t_phys, stride]; CELL_MAJOR: [ncell, stride]).  Pinned TIME_MAJOR arrays
-    are read in place by the kernel (zero-copy); otherwise time chunks are copied (pinned:
-    asynchronously at PCIe speed; pageable: through the driver's staging).
-    Returns a CUDA tensor [n_out, R, T].
+    (TIME_MAJOR: [t_phys, stride]; CELL_MAJOR: [ncell, stride]).
+
+    * compact plan (the default for TIME_MAJOR host inputs): time chunks are PACKED on the
+      host (``ctb_host_pack``, all cores) into pinned staging buffers that hold only the
+      referenced gridcells, copied asynchronously and reduced while the next chunk is packed;
+    * full-grid plan: time chunks are copied whole (pinned: asynchronously at PCIe speed;
+      pageable: through the driver's staging), or -- opt-in, pinned arrays only -- read in
+      place by the kernel (zero-copy).
     """
     dev = plan.device
     out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
     if T == 0 or plan.R == 0:
         return out
+    if layout == N.LAYOUT_CELL_MAJOR:
+        d = [torch.from_numpy(x).to(dev, non_blocking=True) for x in xs]
+        return aggregate_device(plan, d[0], d[1] if len(d) > 1 else None, layout, stride, tix, T,
+                                kind, params, n_out, variant, out=out)
     if zero_copy is None:
         # opt-in: on the round-1 box the in-place read moved 2.5 GB at ~7 GB/s (16-byte requests
         # over PCIe) and lost to copying all 6 GB at ~21 GB/s (profiles/r1_e2e_notes.md)
         zero_copy = os.environ.get("CTB_ZERO_COPY", "0") == "1"
-    if zero_copy and layout == N.LAYOUT_TIME_MAJOR and (variant & 0xff) != N.VARIANT_DIRECT \
+    if zero_copy and not plan.compact and (variant & 0xff) != N.VARIANT_DIRECT \
             and xs[0].dtype in _NP2CTB and _all_pinned(xs):
         # pinned (mapped) host arrays: the kernel reads them in place over PCIe, so only the
         # referenced gridcells (~30 % of a global land/ocean grid) cross the bus
         return _launch(plan, xs[0].ctypes.data, xs[1].ctypes.data if len(xs) > 1 else 0,
                        _NP2CTB[xs[0].dtype], layout, stride, tix, T, kind, params, n_out,
                        N.VARIANT_STAGED | 0x100, out, 0, None, None)
-    ts = [torch.from_numpy(x) for x in xs]
-    if layout == N.LAYOUT_CELL_MAJOR:
-        d = [t.to(dev, non_blocking=True) for t in ts]
-        return aggregate_device(plan, d[0], d[1] if len(d) > 1 else None, layout, stride, tix, T,
-                                kind, params, n_out, variant, out=out)
-    # TIME_MAJOR: chunk over output days; each chunk needs planes [lo, hi] of the input
-    tix_full = np.arange(T, dtype=np.int64) if tix is None else np.asarray(tix, dtype=np.int64)
-    plane_bytes = xs[0].shape[1] * xs[0].dtype.itemsize * len(xs)
-    days = max(32, int(chunk_bytes // max(plane_bytes, 1)) // 32 * 32)
+
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     copy_stream.wait_stream(main)
-    bufs, free_ev = {}, {}
+    tix_full = None if tix is None else np.ascontiguousarray(tix, dtype=np.int64)
+    itemsize = xs[0].dtype.itemsize
+    width = plan.info["n_packed_cells"] if plan.compact else xs[0].shape[1]
+    days = max(32, int(chunk_bytes // max(width * itemsize * len(xs), 1)) // 32 * 32)
     ws = None
     ws_bytes = N.lib().ctb_aggregate_workspace_bytes(plan._h, min(days, T), n_out)
     if ws_bytes:
         ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
+    tdt = torch.float32 if itemsize == 4 else torch.float64
+    dbuf, free_ev, h2d_ev = {}, {}, {}
+    ts = None if plan.compact else [torch.from_numpy(x) for x in xs]
     for ci, t0 in enumerate(range(0, T, days)):
         t1 = min(T, t0 + days)
-        sub = tix_full[t0:t1]
-        lo, hi = int(sub.min()), int(sub.max()) + 1
+        n = t1 - t0
         slot = ci % 2
+        rel = None
+        if plan.compact:
+            # pack on the host (all cores, GIL released) while the previous chunk is in flight
+            if slot in h2d_ev:
+                h2d_ev[slot].synchronize()          # the pinned buffer is free again
+            pins = []
+            for k, x in enumerate(xs):
+                pb = _pinned_buffer((slot, k), days * width * itemsize)
+                N.check(N.lib().ctb_host_pack(
+                    plan._h, C.c_void_p(x.ctypes.data), _NP2CTB[x.dtype], int(stride),
+                    tix_full.ctypes.data_as(C.POINTER(C.c_int64)) if tix_full is not None else None,
+                    int(t0), int(n), C.c_void_p(pb.data_ptr()), int(threads)))
+                pins.append(pb[: n * width * itemsize].view(tdt).view(n, width))
+            srcs = pins
+        else:
+            sub = np.arange(t0, t1) if tix_full is None else tix_full[t0:t1]
+            lo, hi = int(sub.min()), int(sub.max()) + 1
+            srcs = [t[lo:hi] for t in ts]
+            if tix_full is not None and not np.array_equal(sub - lo, np.arange(n)):
+                rel = sub - lo
         with torch.cuda.stream(copy_stream):
             if slot in free_ev:
                 copy_stream.wait_event(free_ev[slot])
             cur = []
-            for k, t in enumerate(ts):
-                need = (hi - lo, t.shape[1])
-                b = bufs.get((slot, k))
-                if b is None or b.shape[0] < need[0]:
-                    b = torch.empty((max(need[0], days + 8), t.shape[1]), dtype=t.dtype, device=dev)
+            for k, src in enumerate(srcs):
+                b = dbuf.get((slot, k))
+                if b is None or b.shape[0] < src.shape[0]:
+                    b = torch.empty((max(src.shape[0], days + 8), src.shape[1]), dtype=tdt, device=dev)
                     b.record_stream(main)
-                    bufs[(slot, k)] = b
-                b[: need[0]].copy_(t[lo:hi], non_blocking=True)
+                    dbuf[(slot, k)] = b
+                b[: src.shape[0]].copy_(src, non_blocking=True)
                 cur.append(b)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
+            h2d_ev[slot] = ready
         main.wait_event(ready)
-        rel = None if (tix is None) else (sub - lo)
-        if tix is not None and np.array_equal(rel, np.arange(t1 - t0)):
-            rel = None
-        aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, stride, rel,
-                         t1 - t0, kind, params, n_out, variant,
-                         out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
+        aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, width, rel, n, kind,
+                         params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
         ev = torch.cuda.Event()
         ev.record(main)
         free_ev[slot] = ev

@@ -23,13 +23,13 @@ SYMBOLS = (
     "ctb_version", "ctb_last_error", "ctb_launch_count", "ctb_plan_build", "ctb_plan_free",
     "ctb_plan_get_info", "ctb_plan_row_cells", "ctb_plan_den", "ctb_plan_row_weights",
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
-    "ctb_debug_stage_bw", "ctb_debug_cpasync_bw",
+    "ctb_debug_stage_bw", "ctb_debug_cpasync_bw", "ctb_host_pack",
 )
 
 
 class PlanOpts(C.Structure):
     _fields_ = [("stage_bytes_per_cell_day", C.c_int32), ("smem_budget_bytes", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("compact", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class PlanInfo(C.Structure):
@@ -39,7 +39,7 @@ class PlanInfo(C.Structure):
         ("n_pieces", C.c_int64), ("n_pieces_distinct", C.c_int64),
         ("n_split_regions", C.c_int32), ("n_scratch_slots", C.c_int32),
         ("cap_cells", C.c_int32), ("max_bundle_cells", C.c_int32), ("time_block", C.c_int32),
-        ("max_region_rows", C.c_int32), ("max_meta_bytes", C.c_int32), ("reserved_", C.c_int32),
+        ("max_region_rows", C.c_int32), ("max_meta_bytes", C.c_int32), ("n_packed_cells", C.c_int32),
     ]
 
     def as_dict(self):
@@ -89,6 +89,8 @@ def lib():
     L.ctb_debug_stage_bw.argtypes = [p, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.ctb_debug_cpasync_bw.restype = C.c_int
     L.ctb_debug_cpasync_bw.argtypes = [p, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp]
+    L.ctb_host_pack.restype = C.c_int
+    L.ctb_host_pack.argtypes = [p, vp, C.c_int, i64, C.POINTER(C.c_int64), i64, i64, vp, C.c_int]
     _lib = L
     return L
 

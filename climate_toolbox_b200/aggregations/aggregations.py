@@ -155,7 +155,7 @@ def _group_requests(reqs):
 
 
 def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant=N.VARIANT_AUTO,
-                    device=None, smem_budget=0, keep_on_device=False):
+                    device=None, smem_budget=0, keep_on_device=False, pack_host=True):
     lat, lon = _coord_labels(ds, "lat"), _coord_labels(ds, "lon")
     reqs = []
     for name in variables:
@@ -173,9 +173,12 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
                 raise ValueError("inputs of a two-input transform must share shape, dtype and layout")
         grid = E.GridSpec(lat, lon, v0.lat_phys, v0.lon_phys, v0.nlat_phys, v0.nlon_phys)
         dev = device or (v0.data2d.device if v0.on_device else E.default_device())
+        # host-resident (time, lat, lon) inputs go through a compact plan: only the referenced
+        # gridcells are packed on the host and cross PCIe
+        compact = (not v0.on_device) and v0.layout == N.LAYOUT_TIME_MAJOR and pack_host
         plan = E.get_plan(grid, weights, aggwt, agglev, backup_aggwt,
                           stage_bytes=len(views) * v0.elem_bytes, device=dev,
-                          smem_budget=smem_budget)
+                          smem_budget=smem_budget, compact=compact)
         n_out = len(g["names"])
         out = _run_group(plan, views, g["kind"], g["params"], n_out, variant)  # [n_out, R, T]
         # reference dim order: agglev takes the place of the first of (lat, lon)

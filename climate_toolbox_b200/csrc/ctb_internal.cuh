@@ -99,6 +99,11 @@ struct ctb_plan {
   int32_t* d_split_region = nullptr;  // [n_split]
   int32_t* d_split_slot_ptr = nullptr;  // [n_split+1]
 
+  // compact plans: physical piece of every packed piece, as runs of consecutive pieces
+  struct PackRun { int32_t phys_piece, n_pieces, packed_piece; };
+  std::vector<PackRun> h_pack_runs;
+  int compact = 0;
+
   // host mirrors for queries
   std::vector<int32_t> h_row_cell;
   std::vector<double> h_row_w;

@@ -396,6 +396,40 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   }
   P->nnz = (int64_t)col.size();
 
+  // region centroids (physical grid coordinates) order the regions along a Hilbert curve
+  std::vector<double> cen_i(R, 0.0), cen_j(R, 0.0);
+  for (int32_t r = 0; r < R; ++r) {
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+      cen_i[r] += col[k] / nlon_phys;
+      cen_j[r] += col[k] % nlon_phys;
+    }
+    const int32_t n = row_ptr[r + 1] - row_ptr[r];
+    if (n) { cen_i[r] /= n; cen_j[r] /= n; }
+  }
+
+  // ---- compact plans: renumber the referenced 4-cell pieces densely ----
+  int64_t plan_ncell = ncell;
+  P->compact = opts && opts->compact ? 1 : 0;
+  if (P->compact) {
+    std::vector<int32_t> cp;
+    cp.reserve(col.size());
+    for (int32_t c : col) cp.push_back(c / CTB_PIECE);
+    std::sort(cp.begin(), cp.end());
+    cp.erase(std::unique(cp.begin(), cp.end()), cp.end());
+    for (auto& c : col) {
+      const int32_t rank = (int32_t)(std::lower_bound(cp.begin(), cp.end(), c / CTB_PIECE) - cp.begin());
+      c = rank * CTB_PIECE + c % CTB_PIECE;
+    }
+    for (size_t q = 0; q < cp.size();) {
+      size_t e = q + 1;
+      while (e < cp.size() && cp[e] == cp[e - 1] + 1) ++e;
+      P->h_pack_runs.push_back({cp[q], (int32_t)(e - q), (int32_t)q});
+      q = e;
+    }
+    plan_ncell = (int64_t)cp.size() * CTB_PIECE;
+    P->ncell = plan_ncell;   // what the kernels index
+  }
+
   // ---- staging bundles ----
   int32_t bytes_cd = opts && opts->stage_bytes_per_cell_day > 0 ? opts->stage_bytes_per_cell_day : 4;
   // shared memory of one CTA = CTB_TILE_STAGES tiles + CTB_META_SLOTS metadata slots; a
@@ -426,22 +460,16 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
       empty_regions.push_back(r);
       continue;
     }
-    double ci = 0, cj = 0;
-    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
-      ci += col[k] / nlon_phys;
-      cj += col[k] % nlon_phys;
-    }
-    const int32_t n = row_ptr[r + 1] - row_ptr[r];
     regs.push_back({r, row_ptr[r], row_ptr[r + 1],
-                    hilbert_xy2d(hn, (uint32_t)(cj / n), (uint32_t)(ci / n))});
+                    hilbert_xy2d(hn, (uint32_t)cen_j[r], (uint32_t)cen_i[r])});
   }
   std::stable_sort(regs.begin(), regs.end(),
                    [](const Region& a, const Region& b) { return a.hkey < b.hkey; });
 
-  const int64_t npiece_grid = (ncell + CTB_PIECE - 1) / CTB_PIECE;
+  const int64_t npiece_grid = (plan_ncell + CTB_PIECE - 1) / CTB_PIECE;
   std::vector<int32_t> stamp(npiece_grid, -1);   // piece -> bundle generation that holds it
   std::vector<uint8_t> seen(npiece_grid, 0);     // piece referenced at all
-  std::vector<uint8_t> cell_seen(ncell, 0);
+  std::vector<uint8_t> cell_seen(plan_ncell, 0);
   int32_t gen = 0;
   std::vector<int32_t> split_region, split_slot_ptr{0};
   int32_t n_scratch = 0;
@@ -550,6 +578,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   I.n_pieces_distinct = pieces_distinct; I.n_split_regions = P->n_split;
   I.n_scratch_slots = n_scratch; I.cap_cells = tile_cap / (CTB_S * bytes_cd); I.max_bundle_cells = B.max_cells;
   I.max_meta_bytes = B.max_meta;
+  I.n_packed_cells = P->compact ? (int32_t)plan_ncell : 0;
   I.time_block = CTB_TB; I.max_region_rows = max_rows;
   CTB_CUDA(cudaDeviceSynchronize());
   return CTB_OK;
@@ -606,5 +635,44 @@ extern "C" int ctb_plan_den(const ctb_plan* plan, double* out) {
 extern "C" int ctb_plan_row_weights(const ctb_plan* plan, double* out) {
   if (!plan || !out) { ctb_set_error("null argument"); return CTB_ERR_INVALID; }
   std::memcpy(out, plan->h_row_w.data(), plan->h_row_w.size() * sizeof(double));
+  return CTB_OK;
+}
+
+// ---------------------------------------------------------------- host ingest ---
+#include <thread>
+
+extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_t stride,
+                             const int64_t* time_index, int64_t t_begin, int64_t T, void* dst,
+                             int n_threads) {
+  if (!P || !x || (!dst && T > 0) || T < 0 || !P->compact) {
+    ctb_set_error("ctb_host_pack: needs a compact plan and non-null buffers");
+    return CTB_ERR_INVALID;
+  }
+  if (dtype != CTB_F32 && dtype != CTB_F64) { ctb_set_error("dtype=%d unsupported", dtype); return CTB_ERR_INVALID; }
+  const size_t es = dtype == CTB_F32 ? 4 : 8;
+  const size_t piece_bytes = CTB_PIECE * es;
+  const int64_t packed = P->ncell;   // cells per packed plane
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(T, 1));
+  const char* src = static_cast<const char*>(x);
+  char* out = static_cast<char*>(dst);
+  auto work = [&](int64_t d0, int64_t d1) {
+    for (int64_t d = d0; d < d1; ++d) {
+      const int64_t tp = time_index ? time_index[t_begin + d] : t_begin + d;
+      const char* plane = src + (size_t)tp * stride * es;
+      char* o = out + (size_t)d * packed * es;
+      for (const auto& r : P->h_pack_runs)
+        std::memcpy(o + (size_t)r.packed_piece * piece_bytes, plane + (size_t)r.phys_piece * piece_bytes,
+                    (size_t)r.n_pieces * piece_bytes);
+    }
+  };
+  if (n_threads == 1) { work(0, T); return CTB_OK; }
+  std::vector<std::thread> pool;
+  const int64_t per = (T + n_threads - 1) / n_threads;
+  for (int i = 0; i < n_threads; ++i) {
+    const int64_t d0 = i * per, d1 = std::min<int64_t>(T, d0 + per);
+    if (d0 < d1) pool.emplace_back(work, d0, d1);
+  }
+  for (auto& th : pool) th.join();
   return CTB_OK;
 }

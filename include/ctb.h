@@ -70,7 +70,10 @@ typedef struct ctb_plan_opts {
                                        tile: n_in * sizeof(elem); default 4 (one f32) */
   int32_t smem_budget_bytes;        /* staging shared memory per CTA; default 72 KiB
                                        (three CTAs per SM) */
-  int32_t reserved[6];
+  int32_t compact;                  /* 1: the plan addresses a PACKED input [T][n_packed_cells]
+                                       holding only the referenced 4-cell pieces (what
+                                       ctb_host_pack writes) instead of the full grid */
+  int32_t reserved[5];
 } ctb_plan_opts;
 
 typedef struct ctb_plan_info {
@@ -89,7 +92,7 @@ typedef struct ctb_plan_info {
   int32_t time_block;      /* days per staging tile */
   int32_t max_region_rows; /* largest region, in kept rows */
   int32_t max_meta_bytes;  /* largest per-bundle metadata blob + piece list, bytes */
-  int32_t reserved_;
+  int32_t n_packed_cells;  /* compact plans: cells per packed plane (4 * distinct pieces), else 0 */
 } ctb_plan_info;
 
 /* ---- misc ---------------------------------------------------------------- */
@@ -163,6 +166,14 @@ int ctb_transform(const void* x0, const void* x1, int dtype, int64_t n, int tran
  * CELL_MAJOR: out[k*T + t]      = x[cell_k*stride + time_index[t]]   (out dtype = in dtype) */
 int ctb_gather_rows(const ctb_plan* plan, const void* x, int dtype, int layout, int64_t stride,
                     const int32_t* time_index, int64_t T, void* out, void* stream);
+
+/* ---- host ingest for compact plans ---------------------------------------- *
+ * Packs the referenced gridcells of `T` day-planes of a HOST array x[t_phys][stride] (dtype
+ * CTB_F32/F64, TIME_MAJOR) into dst[T][n_packed_cells] (HOST, ideally pinned), multi-threaded.
+ * Only ~U/ncell of the input (30 % of a global land/ocean grid) then has to cross PCIe.
+ * time_index (HOST int64, nullable) selects the physical planes.  n_threads <= 0: all cores. */
+int ctb_host_pack(const ctb_plan* plan, const void* x, int dtype, int64_t stride,
+                  const int64_t* time_index, int64_t t_begin, int64_t T, void* dst, int n_threads);
 
 /* ---- diagnostics ---------------------------------------------------------- *
  * Loads-only replay of the staging traffic of ctb_aggregate (TIME_MAJOR, f32) on the

@@ -173,25 +173,35 @@ def test_config1_shape_areawt(where, variant):
     check(out.tas.values, ref, scale)
 
 
-@pytest.mark.parametrize("mode", ["zero_copy_pinned", "chunked_pinned", "chunked_pageable"])
+@pytest.mark.parametrize("mode", ["packed_pageable", "packed_pinned_leap", "zero_copy_pinned",
+                                  "chunked_pinned", "chunked_pageable"])
 def test_host_input_paths(mode):
-    """Host arrays: pinned memory is read in place by the kernel (zero-copy over PCIe); the
-    fallback copies time chunks double-buffered against the kernel.  70 days with a 1 MB chunk
-    budget forces several chunks and a ragged last one."""
+    """Host arrays.  Default: a compact plan -- the referenced gridcells are packed on the host
+    (ctb_host_pack) and only they cross PCIe.  Alternatives: whole time chunks copied
+    double-buffered against the kernel, or pinned memory read in place by the kernel.
+    70 days with a 1 MB chunk budget forces several chunks and a ragged last one."""
     lat, lon, df, tas, _, _ = _config(1.0, 3000, 70)
-    if mode != "chunked_pageable":
+    if "pinned" in mode:
         host = torch.empty(tas.shape, dtype=torch.float32, pin_memory=True)
         host.copy_(torch.from_numpy(tas))
         arr = host.numpy()
     else:
         arr = tas
+    tix = None
+    exp_in = tas
+    if mode.endswith("leap"):
+        tix = np.delete(np.arange(70), [3, 40])        # a time take folded into the packing
+        exp_in = tas[tix]
+    T = exp_in.shape[0]
     grid = E.GridSpec(lat, lon)
-    plan = E.get_plan(grid, df, "areawt", "hierid")
+    plan = E.get_plan(grid, df, "areawt", "hierid", compact=mode.startswith("packed"))
+    if mode.startswith("packed"):
+        assert plan.info["n_packed_cells"] == 4 * plan.info["n_pieces_distinct"] < len(lat) * len(lon)
     n0 = E.launch_count()
     out = E.aggregate_host(plan, [arr.reshape(70, -1)], N.LAYOUT_TIME_MAJOR, arr.shape[1] * arr.shape[2],
-                           None, 70, chunk_bytes=1 << 20, zero_copy=(mode == "zero_copy_pinned"))
+                           tix, T, chunk_bytes=1 << 20, zero_copy=(mode == "zero_copy_pinned"))
     assert (E.launch_count() - n0 == 1) == (mode == "zero_copy_pinned")
-    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "areawt", "hierid")
+    ref, rd, labels, scale = oracle_agg(exp_in, ("time", "lat", "lon"), lat, lon, df, "areawt", "hierid")
     check(out[0].cpu().numpy().T, ref, scale)
 
 
