@@ -27,12 +27,9 @@ def run(lanes_p=8, unr=8, warps=16, cps=2):
         ms.append(e0.elapsed_time(e1))
     return nbytes / min(ms) / 1e6, min(ms)
 print("bundles", plan.info["n_bundles"])
-os.environ["CTB_DBG_ORDER"] = "8"
-for smem, cfgs in ((0, ((8, 24, 1), (4, 24, 1), (8, 32, 1), (8, 16, 2), (8, 8, 4), (4, 8, 4), (8, 8, 3), (8, 12, 2))),
-                   (162000, ((8, 24, 1), (4, 24, 1), (8, 32, 1))),
-                   (80000, ((8, 16, 2), (4, 16, 2), (8, 12, 2))),
-                   (53000, ((8, 8, 3), (8, 10, 3))),
-                   (40000, ((8, 8, 4), (4, 8, 4)))):
-    os.environ["CTB_DBG_SMEM"] = str(smem)
-    for unr, warps, cps in cfgs:
-        print("smem/CTA", smem, "unr", unr, "warps", warps, "cps", cps, "GB/s %.0f  ms %.3f" % run(8, unr, warps, cps), flush=True)
+os.environ["CTB_DBG_ORDER"] = "2"
+os.environ["CTB_DBG_SMEM"] = "76000"
+for sync in (0, 1):
+    os.environ["CTB_DBG_SYNC"] = str(sync)
+    for unr, warps, cps in ((8, 16, 2), (4, 16, 2), (8, 8, 2)):
+        print("barrier per tile", sync, "unr", unr, "warps", warps, "cps", cps, "GB/s %.0f  ms %.3f" % run(8, unr, warps, cps), flush=True)

@@ -7,15 +7,14 @@
 // Fused kernel (TIME_MAJOR input [T][lat][lon], the BCSD layout): CTAs of 16 warps, two per
 // SM, each looping over work units handed out by an atomic counter.  A work unit = one
 // bundle (spatially adjacent regions whose gridcell footprint fits a shared-memory tile) x a
-// chunk of 4 consecutive 32-day blocks, in chunk-major order so that CTAs running together
+// chunk of 2 consecutive 32-day blocks, in chunk-major order so that CTAs running together
 // read neighbouring bundles of the same days (shared lines meet in L2).
 //   metadata: the bundle's piece list, segment table, weights and staged-cell indices arrive
 //           as ONE bulk async copy (cp.async.bulk, TMA 1-D) signalled on an mbarrier, once
 //           per unit;
 //   stage : 16-byte coalesced global loads of the footprint's 4-cell pieces for 32
 //           day-planes, 8 in flight per thread, written TRANSPOSED into smem as a cell-major
-//           tile sx[cell][day] (row stride 33 words => conflict-free both ways); while a tile
-//           is staged the same footprint of the next block is prefetched into L2;
+//           tile sx[cell][day] (row stride 33 words => conflict-free both ways);
 //   gather: one warp per region, lane = day; per 4 CSR entries three vector LDS of
 //           metadata + four conflict-free LDS of data, fp64 FMA, NaN products skipped;
 //           out[r][t] = acc / den[r], 256-byte coalesced stores along time.
@@ -56,7 +55,6 @@ struct AggArgs {
   int n_tb;         // time blocks: ceil(T / 32)
   int chunk_tb;     // time blocks per work unit (a CTA keeps one bundle for a whole unit)
   int* work_counter; // device counter for dynamic unit scheduling (zeroed per launch)
-  int no_prefetch;  // inputs live in mapped host memory: no L2 prefetch
   int dbg;          // CTB_DEBUG bits (perf experiments): 1 skip loads, 2 skip STS, 4 skip gather
   const int32_t *row_ptr, *col;
   const double* w;
@@ -159,8 +157,7 @@ agg_fused_kernel(const AggArgs a) {
   // Work unit = (bundle, chunk of `chunk_tb` consecutive 32-day blocks), handed out by an
   // atomic counter in chunk-major order: CTAs running together work on neighbouring bundles
   // of the same days (shared lines meet in L2), and the bundle's metadata is fetched once
-  // per unit.  While a tile is staged, the same footprint of the NEXT block is prefetched
-  // into L2, so all but the first tile of a unit read L2-resident data.
+  // per unit.
   for (int n_done = 0;; ++n_done) {
   __syncthreads();   // previous unit fully reduced: tile, blob and s_unit may be reused
   if (tid == 0) {
@@ -197,10 +194,6 @@ agg_fused_kernel(const AggArgs a) {
       const int64_t tp = a.tix ? a.tix[t] : t;
       const TIN* p0 = reinterpret_cast<const TIN*>(a.x0) + tp * a.stride;
       const TIN* p1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) + tp * a.stride : p0;
-      // the same footprint one time block later: prefetched into L2 now, staged next iteration
-      const int tn = t + CTB_TB;
-      const bool pf = tn < a.T && tb + 1 < tb_end && !a.no_prefetch && !(a.dbg & 8);
-      const int64_t pf_delta = pf ? ((a.tix ? (int64_t)a.tix[tn] : (int64_t)tn) - tp) * a.stride : 0;
       TIN* sx = reinterpret_cast<TIN*>(smem_raw) + dl;
       for (int g0 = l8 + 8 * sub; g0 < n_units; g0 += 8 * NSUB * TILE_LOADS) {
         int off[TILE_LOADS];
@@ -219,7 +212,6 @@ agg_fused_kernel(const AggArgs a) {
           if (off[u] >= 0) {
             const int o = off[u] & ~(1 << 30);
             const TIN* src = (NIN == 2 && (off[u] >> 30)) ? p1 + o : p0 + o;
-            if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + pf_delta));
             if constexpr (VEC) {
               asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                            : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "l"(src));
@@ -423,7 +415,7 @@ int launch_staged(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
   const int by_smem = (int)((164 * 1024) / (smem + 1024 + 64));
   const int ctas_per_sm = std::max(1, std::min(2, by_smem));
   const int n_tb = (a.T + CTB_TB - 1) / CTB_TB;
-  int chunk_tb = 4;
+  int chunk_tb = 2;
   if (const char* e = getenv("CTB_CHUNK_TB")) chunk_tb = std::max(1, atoi(e));
   const int n_chunks = (n_tb + chunk_tb - 1) / std::max(chunk_tb, 1);
   chunk_tb = n_chunks ? (n_tb + n_chunks - 1) / n_chunks : 1;
@@ -567,9 +559,7 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
   int rc = ctb_pack_transform(transform, params, n_params, n_out, &a.tr);
   if (rc) return rc;
   if (ctb_tr_nin(transform) == 2 && !x1) { ctb_set_error("transform needs two inputs"); return CTB_ERR_INVALID; }
-  // bit 8 of `variant`: do not prefetch the next block into L2 (inputs in mapped host memory)
-  const bool no_prefetch = (variant & 0x100) != 0;
-  variant &= 0xff;
+  variant &= 0xff;   // bit 8 (inputs in mapped host memory) needs no special handling
   if (variant == 0) variant = (layout == CTB_LAYOUT_TIME_MAJOR) ? 1 : 2;
   if (variant != 2 && layout != CTB_LAYOUT_TIME_MAJOR) { ctb_set_error("staged variant needs TIME_MAJOR input"); return CTB_ERR_INVALID; }
   if (variant != 1 && variant != 2) { ctb_set_error("variant=%d unsupported", variant); return CTB_ERR_INVALID; }
@@ -589,7 +579,6 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
   a.b_blob_off = P->d_b_blob_off; a.blob = P->d_blob; a.b_desc = P->d_b_desc; a.row_ptr = P->d_row_ptr; a.col = P->d_col;
   a.w = P->d_w; a.split_region = P->d_split_region; a.split_slot_ptr = P->d_split_slot_ptr;
   a.n_split = P->n_split;
-  a.no_prefetch = no_prefetch ? 1 : 0;
   const size_t es = dtype == CTB_F32 ? 4 : 8;
   const bool vec = (P->ncell % CTB_PIECE == 0) && ((stride * es) % 16 == 0) &&
                    ((uintptr_t)x0 % 16 == 0) && (!x1 || (uintptr_t)x1 % 16 == 0);
@@ -609,7 +598,7 @@ template <int UNR>
 __global__ void debug_stage_bw_kernel(const float* __restrict__ x, int64_t stride, int T,
                                       const int64_t* __restrict__ b_blob_off,
                                       const unsigned char* __restrict__ blob, int n_bundles,
-                                      int n_items, int lanes_p, float* sink, int pf_blocks, int order_chunk) {
+                                      int n_items, int lanes_p, float* sink, int pf_blocks, int order_chunk, int sync_mode) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int lp = lane % lanes_p, ld = lane / lanes_p, dpw = 32 / lanes_p, ndg = 32 / dpw;
   float acc = 0.f;
@@ -648,6 +637,7 @@ __global__ void debug_stage_bw_kernel(const float* __restrict__ x, int64_t strid
 #pragma unroll
       for (int k = 0; k < UNR; ++k) acc += v[k].x + v[k].y + v[k].z + v[k].w;
     }
+    if (sync_mode) __syncthreads();   // CTA-wide barrier per tile, like the fused kernel
   }
   if (acc == 123.25f) *sink = acc;
 }
@@ -676,9 +666,10 @@ extern "C" int ctb_debug_stage_bw(const ctb_plan* P, const void* x, int64_t stri
   int pf_blocks = 0;
   if (const char* e = getenv("CTB_DBG_SMEM")) dsm = (size_t)atoi(e);
   if (const char* e = getenv("CTB_DBG_PF")) pf_blocks = atoi(e);
-  int order_chunk = 0;
+  int order_chunk = 0, sync_mode = 0;
+  if (const char* e = getenv("CTB_DBG_SYNC")) sync_mode = atoi(e);
   if (const char* e = getenv("CTB_DBG_ORDER")) order_chunk = atoi(e);
-#define CTB_DBG(U) if (dsm) CTB_CUDA(cudaFuncSetAttribute(debug_stage_bw_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); debug_stage_bw_kernel<U><<<grid, warps * 32, dsm, st>>>((const float*)x, stride, (int)T, P->d_b_blob_off, P->d_blob, P->n_bundles, (int)n_items, lanes_p, (float*)sink, pf_blocks, order_chunk)
+#define CTB_DBG(U) if (dsm) CTB_CUDA(cudaFuncSetAttribute(debug_stage_bw_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); debug_stage_bw_kernel<U><<<grid, warps * 32, dsm, st>>>((const float*)x, stride, (int)T, P->d_b_blob_off, P->d_blob, P->n_bundles, (int)n_items, lanes_p, (float*)sink, pf_blocks, order_chunk, sync_mode)
   switch (unroll) {
     case 2: CTB_DBG(2); break;
     case 4: CTB_DBG(4); break;
