@@ -15,12 +15,12 @@ df = synthetic.weights_table(0.25, 24378)
 dev = torch.device("cuda", 0)
 x = 288 + 10 * torch.randn((T, len(lat) * len(lon)), dtype=torch.float32, device=dev)
 ref = None
-for budget in (67584, 50688, 44352, 38016, 31680, 25344):
+for budget, threads in ((67584, 512), (50688, 512), (33792, 512)):   # r1_sweep2.log also had 1024-thread CTAs
     plan = E.get_plan(E.GridSpec(lat, lon), df, "popwt", "hierid", smem_budget=budget, cache=False)
     out = torch.empty((1, plan.R, T), dtype=torch.float64, device=dev)
     i = plan.info
     for variant in (1,):
-        for chunk in (2, 4, 8, 16):
+        for chunk in (1, 2, 4):
             os.environ["CTB_CHUNK_TB"] = str(chunk)
             try:
                 for _ in range(3):
@@ -36,8 +36,8 @@ for budget in (67584, 50688, 44352, 38016, 31680, 25344):
                 if ref is None:
                     ref = out.clone()
                 ok = torch.allclose(out, ref, rtol=1e-12, atol=0, equal_nan=True)
-                print("tile %6d B cells %4d bundles %4d staged %6d | variant %d chunk %2d : %.3f ms  ok=%s" %
-                      (budget, i["max_bundle_cells"], i["n_bundles"], i["n_pieces"], variant, chunk, min(ms), ok), flush=True)
+                print("threads %4d tile %6d B cells %4d bundles %4d staged %6d | variant %d chunk %2d : %.3f ms  ok=%s" %
+                      (threads, budget, i["max_bundle_cells"], i["n_bundles"], i["n_pieces"], variant, chunk, min(ms), ok), flush=True)
             except Exception as ex:
                 print("budget", budget, "variant", variant, "failed:", str(ex)[:100], flush=True)
     plan.close()

@@ -7,7 +7,7 @@
 // Fused kernel (TIME_MAJOR input [T][lat][lon], the BCSD layout): CTAs of 16 warps, two per
 // SM, each looping over work units handed out by an atomic counter.  A work unit = one
 // bundle (spatially adjacent regions whose gridcell footprint fits a shared-memory tile) x a
-// chunk of 2 consecutive 32-day blocks, in chunk-major order so that CTAs running together
+// chunk of 4 consecutive 32-day blocks, in chunk-major order so that CTAs running together
 // read neighbouring bundles of the same days (shared lines meet in L2).
 //   metadata: the bundle's piece list, segment table, weights and staged-cell indices arrive
 //           as ONE bulk async copy (cp.async.bulk, TMA 1-D) signalled on an mbarrier, once
@@ -139,7 +139,7 @@ __device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TI
 }
 
 template <typename TIN, int KIND, int NOUT, bool VEC, int THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, (THREADS >= 1024 ? 1 : 2))
 agg_fused_kernel(const AggArgs a) {
   constexpr int NIN = NIn<KIND>::v;
   constexpr int TILE_LOADS = 8;
@@ -413,9 +413,9 @@ int launch_staged(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
   int n_sm = 0;
   CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
   const int by_smem = (int)((164 * 1024) / (smem + 1024 + 64));
-  const int ctas_per_sm = std::max(1, std::min(2, by_smem));
+  const int ctas_per_sm = std::max(1, std::min(THREADS >= 1024 ? 1 : 2, by_smem));
   const int n_tb = (a.T + CTB_TB - 1) / CTB_TB;
-  int chunk_tb = 2;
+  int chunk_tb = 4;
   if (const char* e = getenv("CTB_CHUNK_TB")) chunk_tb = std::max(1, atoi(e));
   const int n_chunks = (n_tb + chunk_tb - 1) / std::max(chunk_tb, 1);
   chunk_tb = n_chunks ? (n_tb + n_chunks - 1) / n_chunks : 1;
