@@ -130,16 +130,38 @@ __device__ __forceinline__ double ctb_ipow(double d, int p) {
 }
 
 // Snyder exceedance degree days, transformations.py:69-89.
-// cos(asin(s)) is evaluated as sqrt((1-s)(1+s)) (identical on [-1,1], no
-// cancellation); asin(|s|>1) stays NaN as in numpy.
-__device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double e) {
+//   tmin < e < tmax :  ((M-e)(pi/2 - asin s) + W cos(asin s)) / pi   with s = (e-M)/W
+//                    = W * g(s),  g(s) = (sqrt(1-s^2) - s*acos(s)) / pi,  g(-a) = g(a) + a
+//   tmax <= e       :  0          (also when tmax is NaN)
+//   tmin >= e       :  M - e      (NaN when tmin is NaN)
+// g is evaluated by two degree-17 polynomials fitted to 80-bit reference values
+// (ctb_edd_coeffs.h, gen_edd_coeffs.py): a <= 1/2 directly, a > 1/2 after factoring the
+// (1-a)^(3/2) behaviour at the end point.  Against asin/cos in numpy the scheme agrees to
+// 4e-16 * max(|EDD|, W); it replaces an fp64 asin, a sqrt and two divisions by ~36 FMAs and
+// one sqrt.  `rW` = 1/W is shared by all thresholds of a gridcell-day.
+#include "ctb_edd_coeffs.h"
+
+__device__ __forceinline__ double ctb_edd_g(double a) {
+  constexpr double A[CTB_EDD_A_N] = CTB_EDD_A_COEFFS;
+  constexpr double B[CTB_EDD_B_N] = CTB_EDD_B_COEFFS;
+  const double v = 1.0 - a;
+  const double ta = fma(4.0, a, -1.0), tb = fma(4.0, v, -1.0);
+  double pa = A[CTB_EDD_A_N - 1], pb = B[CTB_EDD_B_N - 1];
+#pragma unroll
+  for (int k = CTB_EDD_A_N - 2; k >= 0; --k) pa = fma(pa, ta, A[k]);
+#pragma unroll
+  for (int k = CTB_EDD_B_N - 2; k >= 0; --k) pb = fma(pb, tb, B[k]);
+  return a <= 0.5 ? pa : v * sqrt(v) * pb;
+}
+
+__device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double rW,
+                                          double e) {
   double r;
   if (tmin < e) {
     if (tmax > e) {
-      const double s = (e - M) / W;
-      const double th = asin(s);
-      const double c = sqrt(fmax((1.0 - s) * (1.0 + s), 0.0));
-      r = ((M - e) * (1.5707963267948966 - th) + W * c) / 3.141592653589793;
+      const double s = (e - M) * rW, a = fabs(s);
+      const double g = ctb_edd_g(fmin(a, 1.0));
+      r = W * (s < 0.0 ? g + a : g);
     } else {
       r = 0.0;
     }
@@ -170,14 +192,14 @@ __device__ __forceinline__ void ctb_apply(const CtbTr& P, double x0, double x1, 
       for (int j = 0; j < NOUT; ++j) f[j] = ctb_ipow(d, P.ip[j]);
     }
   } else if constexpr (KIND == CTB_TR_EDD) {
-    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2;
+    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2, rW = 1.0 / W;
 #pragma unroll
-    for (int j = 0; j < NOUT; ++j) f[j] = ctb_edd(x0, x1, M, W, P.a[j]);
+    for (int j = 0; j < NOUT; ++j) f[j] = ctb_edd(x0, x1, M, W, rW, P.a[j]);
   } else {  // GDD
-    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2;
+    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2, rW = 1.0 / W;
 #pragma unroll
     for (int j = 0; j < NOUT; ++j)
-      f[j] = ctb_edd(x0, x1, M, W, P.a[2 * j]) - ctb_edd(x0, x1, M, W, P.a[2 * j + 1]);
+      f[j] = ctb_edd(x0, x1, M, W, rW, P.a[2 * j]) - ctb_edd(x0, x1, M, W, rW, P.a[2 * j + 1]);
   }
 }
 
