@@ -261,6 +261,7 @@ def _all_pinned(xs):
 
 
 _PINNED = {}   # (slot, k) -> pinned staging tensor for packed chunks (reused across calls)
+TRANSFER_BYTES = {"h2d": 0, "d2h": 0}   # bytes actually copied across PCIe by this module (bench e2e)
 
 
 def _pinned_buffer(key, nbytes):
@@ -291,6 +292,7 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
         return out
     if layout == N.LAYOUT_CELL_MAJOR:
         d = [torch.from_numpy(x).to(dev, non_blocking=True) for x in xs]
+        TRANSFER_BYTES["h2d"] += sum(x.nbytes for x in xs)
         return aggregate_device(plan, d[0], d[1] if len(d) > 1 else None, layout, stride, tix, T,
                                 kind, params, n_out, variant, out=out)
     if zero_copy is None:
@@ -354,6 +356,7 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
                     b.record_stream(main)
                     dbuf[(slot, k)] = b
                 b[: src.shape[0]].copy_(src, non_blocking=True)
+                TRANSFER_BYTES["h2d"] += src.numel() * src.element_size()
                 cur.append(b)
             ready = torch.cuda.Event()
             ready.record(copy_stream)

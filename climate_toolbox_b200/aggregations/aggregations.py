@@ -193,6 +193,7 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
             # the returned arrays.
             host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
             host.copy_(out, non_blocking=True)
+            E.TRANSFER_BYTES["d2h"] += out.numel() * out.element_size()
             torch.cuda.current_stream(out.device).synchronize()
             res = host.numpy()
         R = plan.R
