@@ -456,3 +456,73 @@ def test_full_size_properties():
     sl = x[100:103].cpu().numpy()
     ref, rd, labels, scale = oracle_agg(sl, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
     check(y[100:103].cpu().numpy(), ref, scale)
+
+
+# ----------------------------------------------------------------------------
+# randomized parity sweep (small sizes, many shapes)
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_parity(seed):
+    """Random grid sizes (odd and even, so both the 16-byte and the scalar staging paths),
+    dtypes, layouts, time lengths (ragged 32-day blocks), NaN densities, weight holes, region
+    counts from 1 to more than one tile's worth, host and device inputs, random transforms."""
+    rng = np.random.default_rng(1000 + seed)
+    nlat, nlon = int(rng.integers(3, 40)), int(rng.integers(3, 60))
+    if seed % 3 == 0:
+        nlon = (nlon // 4 + 1) * 4                       # aligned planes -> vector loads
+    T = int(rng.choice([1, 2, 31, 32, 33, 64, 77]))
+    dtype = np.float32 if rng.random() < 0.6 else np.float64
+    lat = np.sort(rng.choice(np.arange(-90, 90, 0.25), nlat, replace=False))
+    lon = np.sort(rng.choice(np.arange(-180, 180, 0.25), nlon, replace=False))
+    n_rows = int(rng.integers(1, 4 * nlat * nlon))
+    n_reg = int(rng.integers(1, max(2, n_rows // 3)))
+    wts = rng.lognormal(0, 1, n_rows)
+    wts[rng.random(n_rows) < 0.2] = np.nan
+    wts[rng.random(n_rows) < 0.1] = 0.0
+    area = rng.random(n_rows)
+    area[rng.random(n_rows) < 0.05] = np.nan
+    labels = rng.integers(0, n_reg, n_rows).astype(object)
+    labels[rng.random(n_rows) < 0.03] = np.nan
+    df = pd.DataFrame({"lat": rng.choice(lat, n_rows), "lon": rng.choice(lon, n_rows),
+                       "hierid": labels, "popwt": wts, "areawt": area})
+    x = (280 + 15 * rng.standard_normal((T, nlat, nlon))).astype(dtype)
+    x[rng.random(x.shape) < rng.choice([0.0, 0.01, 0.3])] = np.nan
+    spread = np.abs(4 * rng.standard_normal(x.shape)).astype(dtype)
+    dims = ("time", "lat", "lon")
+    layout_llt = rng.random() < 0.3
+    on_device = rng.random() < 0.5
+
+    def put(a):
+        if layout_llt:
+            a = np.ascontiguousarray(a.transpose(1, 2, 0))
+        return torch.from_numpy(a).cuda() if on_device else a
+
+    d = ("lat", "lon", "time") if layout_llt else dims
+    coords = {"time": np.arange(T), "lat": lat, "lon": lon}
+    kind = ["identity", "poly", "edd", "gdd"][seed % 4]
+    ds = Dataset({"tas": (d, put(x))}, coords=coords)
+    if kind == "identity":
+        f, name = x.astype(np.float64), "tas"
+    elif kind == "poly":
+        p = int(rng.integers(1, 5))
+        from climate_toolbox_b200._xr import Deferred, Variable
+        ds._vars["v"] = Variable(d, None, None, None, Deferred("poly", (273.15, float(p)), (ds._vars["tas"],)))
+        f, name = (x.astype(np.float64) - 273.15) ** p, "v"
+    else:
+        tn = DataArray(put(x - spread), dims=d, coords=coords, attrs={"units": "K"})
+        tx = DataArray(put(x + spread), dims=d, coords=coords, attrs={"units": "K"})
+        lo_, hi_ = 283.15, 291.0
+        if kind == "edd":
+            ds["v"] = snyder_edd(tn, tx, lo_)
+            f = oracle.snyder_edd(x - spread, x + spread, lo_)
+        else:
+            ds["v"] = snyder_gdd(tn, tx, lo_, hi_)
+            f = oracle.snyder_gdd(x - spread, x + spread, lo_, hi_)
+        name = "v"
+    out = weighted_aggregate_grid_to_regions(ds, name, "popwt", "hierid", weights=df)
+    ref, rd, labels_o, scale = oracle_agg(f, dims, lat, lon, df, "popwt", "hierid")
+    got = out[name]
+    assert list(out.hierid.values) == list(labels_o)
+    got_v = got.values if got.dims == rd else got.transpose(*rd).values
+    scale = scale + (np.abs(spread).max() if kind in ("edd", "gdd") else 0.0)
+    check(got_v, ref, scale)
