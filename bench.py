@@ -195,6 +195,8 @@ def run_ours(args):
             raise SystemExit("--gpus {} needs torchrun with {} ranks".format(args.gpus, args.gpus))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:   # ranks share the host cores for the e2e packing
+        os.environ.setdefault("CTB_PACK_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

@@ -307,6 +307,8 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
                        _NP2CTB[xs[0].dtype], layout, stride, tix, T, kind, params, n_out,
                        N.VARIANT_STAGED | 0x100, out, 0, None, None)
 
+    if not threads:
+        threads = int(os.environ.get("CTB_PACK_THREADS", "0"))   # 0 = all cores
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     copy_stream.wait_stream(main)
