@@ -135,7 +135,7 @@ def region_codes(labels):
 
 
 def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4, device=None,
-             smem_budget=0, cache=True, compact=False):
+             smem_budget=0, cache=True, compact=False, elem_bytes=4):
     """Build (or fetch) the device plan for (grid, weights[lat, lon, agglev, aggwt, backup])."""
     device = device or default_device()
     for col in ("lat", "lon", agglev, aggwt, backup_aggwt):
@@ -150,7 +150,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
         grid.digest(gh)
         with np.errstate(all="ignore"):
             fp = (id(weights), len(weights), aggwt, agglev, backup_aggwt, stage_bytes, smem_budget,
-                  bool(compact), str(device), gh.hexdigest(),
+                  bool(compact), int(elem_bytes), str(device), gh.hexdigest(),
                   tuple(float(np.nansum(np.asarray(weights[c].values, dtype=np.float64)))
                         for c in ("lat", "lon", aggwt, backup_aggwt)),
                   str(weights[agglev].values[0]) if len(weights) else "",
@@ -170,7 +170,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     grid.digest(h)
     for a in (row_lat, row_lon, wp, wb, codes):
         h.update(a.tobytes())
-    h.update(repr((stage_bytes, smem_budget, bool(compact), str(device), len(labels))).encode())
+    h.update(repr((stage_bytes, smem_budget, bool(compact), int(elem_bytes), str(device), len(labels))).encode())
     key = h.hexdigest()
     if cache and key in _PLAN_CACHE:
         _PLAN_CACHE.move_to_end(key)
@@ -181,6 +181,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     opts.stage_bytes_per_cell_day = int(stage_bytes)
     opts.smem_budget_bytes = int(smem_budget)
     opts.compact = 1 if compact else 0
+    opts.elem_bytes = int(elem_bytes)
     handle = C.c_void_p()
     bad_row, bad_axis = C.c_int64(-1), C.c_int32(-1)
     rc = N.lib().ctb_plan_build(

@@ -29,7 +29,7 @@ SYMBOLS = (
 
 class PlanOpts(C.Structure):
     _fields_ = [("stage_bytes_per_cell_day", C.c_int32), ("smem_budget_bytes", C.c_int32),
-                ("compact", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("compact", C.c_int32), ("elem_bytes", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class PlanInfo(C.Structure):

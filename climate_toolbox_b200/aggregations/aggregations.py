@@ -178,7 +178,7 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
         compact = (not v0.on_device) and v0.layout == N.LAYOUT_TIME_MAJOR and pack_host
         plan = E.get_plan(grid, weights, aggwt, agglev, backup_aggwt,
                           stage_bytes=len(views) * v0.elem_bytes, device=dev,
-                          smem_budget=smem_budget, compact=compact)
+                          smem_budget=smem_budget, compact=compact, elem_bytes=v0.elem_bytes)
         n_out = len(g["names"])
         out = _run_group(plan, views, g["kind"], g["params"], n_out, variant)  # [n_out, R, T]
         # reference dim order: agglev takes the place of the first of (lat, lon)
@@ -255,7 +255,8 @@ def _reindex_spatial_data_to_regions(ds, df, new_dim="reshape_index"):
         view = _GridView(var)
         grid = E.GridSpec(lat, lon, view.lat_phys, view.lon_phys, view.nlat_phys, view.nlon_phys)
         dev = view.data2d.device if view.on_device else E.default_device()
-        plan = E.get_plan(grid, trivial, "_w", "_r", "_w", stage_bytes=view.elem_bytes, device=dev)
+        plan = E.get_plan(grid, trivial, "_w", "_r", "_w", stage_bytes=view.elem_bytes, device=dev,
+                          elem_bytes=view.elem_bytes)
         first = min(var.dims.index("lat"), var.dims.index("lon"))
         others = [d for d in var.dims if d not in ("lat", "lon")]
         new_dims = list(others)

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "ctb_internal.cuh"
 
@@ -115,18 +116,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// one CSR entry: acc_j += w * f_j(x), NaN products skipped (skipna sum, aggregations.py:78)
-template <typename TIN, int KIND, int NOUT>
+// one CSR entry: acc_j += w * f_j(x), NaN products skipped (skipna sum, aggregations.py:78).
+// CHECK = false: the tile was seen to hold no NaN while it was staged (IDENTITY / POLY only,
+// where f is NaN iff x is).
+template <typename TIN, int KIND, int NOUT, bool CHECK = true>
 __device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TIN r1,
                                            double (&acc)[NOUT]) {
   double f[NOUT];
   if constexpr (KIND == CTB_TR_IDENTITY) {
     // the product is NaN iff x is NaN (w is finite, non-zero): zero it in the storage type
-    const TIN xs = (r0 == r0) ? r0 : TIN(0);
+    const TIN xs = (!CHECK || r0 == r0) ? r0 : TIN(0);
     acc[0] = fma(w, (double)xs, acc[0]);
   } else if constexpr (KIND == CTB_TR_POLY) {
     ctb_apply<KIND, NOUT>(tr, (double)r0, (double)r1, f);
-    if (r0 == r0) {   // f is NaN iff x is NaN: one compare gates all outputs
+    if (!CHECK || r0 == r0) {   // f is NaN iff x is NaN: one compare gates all outputs
 #pragma unroll
       for (int j = 0; j < NOUT; ++j) acc[j] = fma(w, f[j], acc[j]);
     }
@@ -149,6 +152,7 @@ agg_fused_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_unit;
+  __shared__ int s_nan[2];   // a NaN was staged into the tile (by tile parity)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* const s_blob = smem_raw + a.tile_stride;
@@ -161,6 +165,7 @@ agg_fused_kernel(const AggArgs a) {
   for (int n_done = 0;; ++n_done) {
   __syncthreads();   // previous unit fully reduced: tile, blob and s_unit may be reused
   if (tid == 0) {
+    s_nan[0] = s_nan[1] = 0;
     s_unit = atomicAdd(a.work_counter, 1);
     if (s_unit < a.n_items) {
       const int4 d = __ldg(a.b_desc + s_unit % a.n_bundles);
@@ -232,6 +237,25 @@ agg_fused_kernel(const AggArgs a) {
             }
           }
         }
+        if constexpr (KIND == CTB_TR_IDENTITY) {
+          bool nan = false;
+#pragma unroll
+          for (int u = 0; u < TILE_LOADS; ++u) {
+            if (off[u] >= 0) {
+              if constexpr (sizeof(TIN) == 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float f = __uint_as_float(v[u][q]); nan |= (f != f); }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const double f = __longlong_as_double(((long long)v[u][2 * q + 1] << 32) | v[u][2 * q]);
+                  nan |= (f != f);
+                }
+              }
+            }
+          }
+          if (nan) s_nan[(tb - tb_begin) & 1] = 1;
+        }
 #pragma unroll
         for (int u = 0; u < TILE_LOADS; ++u) {
           const int g = g0 + 8 * NSUB * u;
@@ -256,10 +280,14 @@ agg_fused_kernel(const AggArgs a) {
   // ---------------- gather + segmented weighted sum: warp = region, lane = day ------------
   const CtbSeg* segs = reinterpret_cast<const CtbSeg*>(mb + H.off_seg);
   const double* W = reinterpret_cast<const double*>(mb + H.off_w);
-  const uint16_t* LOC = reinterpret_cast<const uint16_t*>(mb + H.off_loc);
-  const TIN* sx0 = reinterpret_cast<const TIN*>(smem_raw) + lane;
-  const TIN* sx1 = sx0 + (size_t)nP * CTB_PIECE * S;
+  const uint32_t* OFF = reinterpret_cast<const uint32_t*>(mb + H.off_loc);   // byte offsets of staged cells
+  const unsigned char* sb0 = smem_raw + lane * sizeof(TIN);
+  const unsigned char* sb1 = sb0 + (size_t)nP * CTB_PIECE * S * sizeof(TIN);
   const int t = t0 + lane;
+  auto at0 = [&](uint32_t o) { return *reinterpret_cast<const TIN*>(sb0 + o); };
+  auto at1 = [&](uint32_t o) { return *reinterpret_cast<const TIN*>(sb1 + o); };
+  const bool tile_nan = s_nan[(tb - tb_begin) & 1] != 0;
+  if (tid == 0) s_nan[(tb - tb_begin + 1) & 1] = 0;   // flag of the next tile (nobody reads it now)
   // segments are sorted longest-first: round-robin over the warps is balanced
   for (int s = warp; s < ((a.dbg & 4) ? 0 : H.n_seg); s += (THREADS / 32)) {
     const CtbSeg sg = segs[s];
@@ -277,14 +305,13 @@ agg_fused_kernel(const AggArgs a) {
       double wA[4];
       TIN xA[4], yA[4];
       auto fetch = [&](int e, double (&w)[4], TIN (&x0)[4], TIN (&x1)[4]) {
-        const uint2 lc = *reinterpret_cast<const uint2*>(LOC + e);
+        const uint4 o = *reinterpret_cast<const uint4*>(OFF + e);
         const double2 w01 = *reinterpret_cast<const double2*>(W + e);
         const double2 w23 = *reinterpret_cast<const double2*>(W + e + 2);
         w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
-        const int l0 = lc.x & 0xffff, l1 = lc.x >> 16, l2 = lc.y & 0xffff, l3 = lc.y >> 16;
-        x0[0] = sx0[l0 * S]; x0[1] = sx0[l1 * S]; x0[2] = sx0[l2 * S]; x0[3] = sx0[l3 * S];
+        x0[0] = at0(o.x); x0[1] = at0(o.y); x0[2] = at0(o.z); x0[3] = at0(o.w);
         if constexpr (NIN == 2) {
-          x1[0] = sx1[l0 * S]; x1[1] = sx1[l1 * S]; x1[2] = sx1[l2 * S]; x1[3] = sx1[l3 * S];
+          x1[0] = at1(o.x); x1[1] = at1(o.y); x1[2] = at1(o.z); x1[3] = at1(o.w);
         } else {
           x1[0] = x1[1] = x1[2] = x1[3] = TIN(0);
         }
@@ -312,25 +339,32 @@ agg_fused_kernel(const AggArgs a) {
       }
     } else {
       // plain aggregation / polynomials: 64-register CTAs have no room for the pipelined
-      // form (it spills and measured 20 % slower); two chunks per iteration instead
+      // form (it spills and measured 20 % slower); two chunks per iteration instead.  The
+      // metadata LDS feeds the data LDS directly (byte offsets are baked into the plan), and
+      // tiles that were staged without a NaN skip the per-value check.
       const int e0 = (int)sg.e0_4 * 4;
       const int e_full = e0 + ((int)sg.n & ~3), e_end = e0 + (int)sg.n;
+      auto body = [&](auto check) {
+        constexpr bool CHECK = decltype(check)::value;
 #pragma unroll 2
-      for (int e = e0; e < e_full; e += 4) {
-        const uint2 lc = *reinterpret_cast<const uint2*>(LOC + e);
-        const double2 w01 = *reinterpret_cast<const double2*>(W + e);
-        const double2 w23 = *reinterpret_cast<const double2*>(W + e + 2);
-        const int l0 = lc.x & 0xffff, l1 = lc.x >> 16, l2 = lc.y & 0xffff, l3 = lc.y >> 16;
-        TIN r0[4], r1[4];
-        r0[0] = sx0[l0 * S]; r0[1] = sx0[l1 * S]; r0[2] = sx0[l2 * S]; r0[3] = sx0[l3 * S];
-        r1[0] = r1[1] = r1[2] = r1[3] = TIN(0);
-        accumulate<TIN, KIND, NOUT>(a.tr, w01.x, r0[0], r1[0], acc);
-        accumulate<TIN, KIND, NOUT>(a.tr, w01.y, r0[1], r1[1], acc2);
-        accumulate<TIN, KIND, NOUT>(a.tr, w23.x, r0[2], r1[2], acc);
-        accumulate<TIN, KIND, NOUT>(a.tr, w23.y, r0[3], r1[3], acc2);
+        for (int e = e0; e < e_full; e += 4) {
+          const uint4 o = *reinterpret_cast<const uint4*>(OFF + e);
+          const double2 w01 = *reinterpret_cast<const double2*>(W + e);
+          const double2 w23 = *reinterpret_cast<const double2*>(W + e + 2);
+          const TIN x0 = at0(o.x), x1 = at0(o.y), x2 = at0(o.z), x3 = at0(o.w);
+          accumulate<TIN, KIND, NOUT, CHECK>(a.tr, w01.x, x0, TIN(0), acc);
+          accumulate<TIN, KIND, NOUT, CHECK>(a.tr, w01.y, x1, TIN(0), acc2);
+          accumulate<TIN, KIND, NOUT, CHECK>(a.tr, w23.x, x2, TIN(0), acc);
+          accumulate<TIN, KIND, NOUT, CHECK>(a.tr, w23.y, x3, TIN(0), acc2);
+        }
+        for (int e = e_full; e < e_end; ++e)   // ragged tail (< 4 entries)
+          accumulate<TIN, KIND, NOUT, CHECK>(a.tr, W[e], at0(OFF[e]), TIN(0), acc);
+      };
+      if constexpr (KIND == CTB_TR_IDENTITY) {
+        if (tile_nan) body(std::true_type{}); else body(std::false_type{});
+      } else {
+        body(std::true_type{});   // polynomials: one code path (two measured slower)
       }
-      for (int e = e_full; e < e_end; ++e)   // ragged tail (< 4 entries)
-        accumulate<TIN, KIND, NOUT>(a.tr, W[e], sx0[(int)LOC[e] * S], TIN(0), acc);
     }
     if (t < a.T) {
       if (sg.target >= 0) {
@@ -410,6 +444,11 @@ int launch_staged(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
   const size_t tile = ((size_t)NIN * P->info.max_bundle_cells * CTB_S * sizeof(TIN) + 127) & ~(size_t)127;
   const size_t meta = (size_t)CTB_META_A_CAP + (((size_t)P->info.max_meta_bytes + 15) & ~(size_t)15);
   const size_t smem = tile + meta;
+  if (P->elem_bytes != (int)sizeof(TIN)) {
+    ctb_set_error("plan was built for %d-byte elements, input has %d-byte elements: rebuild it with "
+                  "elem_bytes=%d", P->elem_bytes, (int)sizeof(TIN), (int)sizeof(TIN));
+    return CTB_ERR_UNSUPPORTED;
+  }
   int n_sm = 0;
   CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
   const int by_smem = (int)((164 * 1024) / (smem + 1024 + 64));

@@ -41,13 +41,14 @@ constexpr int CTB_STAGE_THREADS = 256; // 8 warps: each stages 4 days x 8 pieces
 
 // Per-bundle metadata blob, copied to shared memory with one cp.async.bulk:
 //   part A: [CtbBlobHeader][n_pieces x int32 piece]
-//   part B: [n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint16 loc]
+//   part B: [n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint32 off]
+//           off = byte offset of the entry's staged cell row in the tile: cell * 33 * elem_bytes
 // (every section 16-byte aligned; every segment's entries start at a multiple of 4;
 //  off_* are byte offsets from the start of part B)
 struct CtbBlobHeader {
   int32_t n_pieces, n_seg;
   int32_t off_seg, off_w, off_loc;  // byte offsets from the start of part B
-  int32_t n_ent_pad, bytes_a, bytes_b;
+  int32_t n_ent_pad, bytes_a, bytes_b;   // off_loc = offset of the uint32 `off` array
 };
 struct CtbSeg {
   int32_t target;  // >= 0: region row of `out`; < 0: ~scratch_slot (region split over bundles)
@@ -103,6 +104,7 @@ struct ctb_plan {
   struct PackRun { int32_t phys_piece, n_pieces, packed_piece; };
   std::vector<PackRun> h_pack_runs;
   int compact = 0;
+  int elem_bytes = 4;   // element size the staged-cell byte offsets were built for
 
   // host mirrors for queries
   std::vector<int32_t> h_row_cell;

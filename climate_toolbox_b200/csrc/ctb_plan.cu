@@ -129,6 +129,7 @@ struct BundleBuilder {
   int32_t max_cells = 0, max_meta = 0, n_segments = 0;
   int64_t n_pieces_total = 0;
   int32_t bytes_cd = 4;       // staged bytes per cell-day
+  int32_t elem_bytes = 4;     // element size of the staged inputs
   int32_t tile_cap = 0;       // bytes of one staging tile
   int32_t meta_cap = 0;       // bytes of one metadata slot
   const double* den = nullptr;
@@ -144,7 +145,7 @@ struct BundleBuilder {
     return (int32_t)sizeof(CtbBlobHeader) + pad(n_pieces * 4, 16);
   }
   static int32_t part_b_bytes(int32_t n_seg, int32_t n_ent_pad) {
-    return n_seg * (int32_t)sizeof(CtbSeg) + 10 * pad(n_ent_pad, 8);
+    return n_seg * (int32_t)sizeof(CtbSeg) + 12 * pad(n_ent_pad, 8);
   }
   int32_t tile_bytes(int32_t n_pieces) const { return n_pieces * CTB_PIECE * CTB_S * bytes_cd; }
   bool fits_counts(int32_t n_pieces, int32_t n_seg, int32_t n_ent_pad) const {
@@ -177,7 +178,7 @@ struct BundleBuilder {
     h.off_w = n_seg * (int32_t)sizeof(CtbSeg);
     h.off_loc = h.off_w + 8 * n_ent_pad;
     h.bytes_a = part_a_bytes(n_p);
-    h.bytes_b = pad(h.off_loc + 2 * n_ent_pad, 16);
+    h.bytes_b = pad(h.off_loc + 4 * n_ent_pad, 16);
     const size_t base = blob.size();
     const size_t bytes = (size_t)h.bytes_a + h.bytes_b;
     blob.resize(base + bytes, 0);
@@ -186,7 +187,7 @@ struct BundleBuilder {
     const size_t bb = base + h.bytes_a;
     CtbSeg* segs = reinterpret_cast<CtbSeg*>(&blob[bb + h.off_seg]);
     double* w = reinterpret_cast<double*>(&blob[bb + h.off_w]);
-    uint16_t* loc = reinterpret_cast<uint16_t*>(&blob[bb + h.off_loc]);
+    uint32_t* loc = reinterpret_cast<uint32_t*>(&blob[bb + h.off_loc]);
     desc.push_back(make_int4((int)(base & 0xffffffffu), (int)(base >> 32), h.bytes_a, h.bytes_b));
     int32_t e = 0;
     for (int32_t i = 0; i < n_seg; ++i) {
@@ -197,7 +198,7 @@ struct BundleBuilder {
         const int32_t piece = s.cols[k] / CTB_PIECE;
         const int32_t lp = (int32_t)(std::lower_bound(cur_pieces.begin(), cur_pieces.end(), piece) -
                                      cur_pieces.begin());
-        loc[e + k] = (uint16_t)(lp * CTB_PIECE + s.cols[k] % CTB_PIECE);
+        loc[e + k] = (uint32_t)(lp * CTB_PIECE + s.cols[k] % CTB_PIECE) * (uint32_t)(CTB_S * elem_bytes);
         w[e + k] = s.ws[k];
       }
       e += pad((int32_t)s.cols.size(), 4);
@@ -440,6 +441,8 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   if (opts && opts->smem_budget_bytes > 0) tile_cap = std::min(tile_cap, opts->smem_budget_bytes);
   BundleBuilder B;
   B.bytes_cd = bytes_cd;
+  B.elem_bytes = opts && opts->elem_bytes == 8 ? 8 : 4;
+  P->elem_bytes = B.elem_bytes;
   B.tile_cap = tile_cap;
   B.meta_cap = meta_cap;
   B.den = P->h_den.data();

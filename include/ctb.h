@@ -73,7 +73,9 @@ typedef struct ctb_plan_opts {
   int32_t compact;                  /* 1: the plan addresses a PACKED input [T][n_packed_cells]
                                        holding only the referenced 4-cell pieces (what
                                        ctb_host_pack writes) instead of the full grid */
-  int32_t reserved[5];
+  int32_t elem_bytes;               /* 4 (default) or 8: element size of the inputs this plan will
+                                       aggregate (staged-cell byte offsets are baked into the plan) */
+  int32_t reserved[4];
 } ctb_plan_opts;
 
 typedef struct ctb_plan_info {
