@@ -194,11 +194,16 @@ agg_fused_kernel(const AggArgs a) {
     constexpr int NSUB = (THREADS / 32) / 8;            // warps sharing one 4-day group
     const int sub = warp >> 3;
     const int t = t0 + dl;
-    const int n_units = nP * HALVES * NIN;         // unit index: [input][piece][half]
+    const int nPH = nP * HALVES;
+    const int n_units = nPH * NIN;                 // unit index: [input][piece][half]
     if (t < a.T && !(a.dbg & 1)) {
       const int64_t tp = a.tix ? a.tix[t] : t;
       const TIN* p0 = reinterpret_cast<const TIN*>(a.x0) + tp * a.stride;
       const TIN* p1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) + tp * a.stride : p0;
+      // keep the day's base pointers in registers: under the 64-register cap the compiler
+      // otherwise rebuilds the 64-bit product in front of every load
+      asm volatile("" : "+l"(p0));
+      if constexpr (NIN == 2) asm volatile("" : "+l"(p1));
       TIN* sx = reinterpret_cast<TIN*>(smem_raw) + dl;
       for (int g0 = l8 + 8 * sub; g0 < n_units; g0 += 8 * NSUB * TILE_LOADS) {
         int off[TILE_LOADS];
@@ -206,24 +211,24 @@ agg_fused_kernel(const AggArgs a) {
 #pragma unroll
         for (int u = 0; u < TILE_LOADS; ++u) {      // all index reads first, then all loads
           const int g = g0 + 8 * NSUB * u;
-          off[u] = -1;
           if (g < n_units) {
-            const int in = g / (nP * HALVES), r = g - in * (nP * HALVES);
-            off[u] = (s_piece[r / HALVES] * CTB_PIECE + (r % HALVES) * CPU) | (in << 30);
+            // no runtime division here: it costs ~35 instructions per load in front of the LDG
+            const int in = (NIN == 2 && g >= nPH) ? 1 : 0, r = g - (in ? nPH : 0);
+            off[u] = s_piece[r / HALVES] * CTB_PIECE + (r % HALVES) * CPU;
           }
         }
 #pragma unroll
         for (int u = 0; u < TILE_LOADS; ++u) {
-          if (off[u] >= 0) {
-            const int o = off[u] & ~(1 << 30);
-            const TIN* src = (NIN == 2 && (off[u] >> 30)) ? p1 + o : p0 + o;
+          const int g = g0 + 8 * NSUB * u;
+          if (g < n_units) {
+            const TIN* src = (NIN == 2 && g >= nPH) ? p1 + off[u] : p0 + off[u];
             if constexpr (VEC) {
               asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                            : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "l"(src));
             } else {
               TIN tv[CPU];
 #pragma unroll
-              for (int q = 0; q < CPU; ++q) tv[q] = (o + q < a.ncell) ? __ldg(src + q) : TIN(0);
+              for (int q = 0; q < CPU; ++q) tv[q] = (off[u] + q < a.ncell) ? __ldg(src + q) : TIN(0);
               if constexpr (sizeof(TIN) == 4) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[u][q] = __float_as_uint((float)tv[q]);
@@ -235,31 +240,38 @@ agg_fused_kernel(const AggArgs a) {
                 }
               }
             }
+          } else {
+            v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0u;   // keeps the NaN scan branch-free
           }
         }
         if constexpr (KIND == CTB_TR_IDENTITY) {
-          bool nan = false;
+          bool nan;
+          if constexpr (sizeof(TIN) == 4) {
+            // NaN-propagating 3-input max over the 32 staged values: 16 instructions
+            float m = __uint_as_float(v[0][0]);
 #pragma unroll
-          for (int u = 0; u < TILE_LOADS; ++u) {
-            if (off[u] >= 0) {
-              if constexpr (sizeof(TIN) == 4) {
+            for (int u = 0; u < TILE_LOADS; ++u)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { const float f = __uint_as_float(v[u][q]); nan |= (f != f); }
-              } else {
+              for (int q = 0; q < 4; q += 2)
+                asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(m)
+                    : "f"(__uint_as_float(v[u][q])), "f"(__uint_as_float(v[u][q + 1])));
+            nan = (m != m);
+          } else {
+            nan = false;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  const double f = __longlong_as_double(((long long)v[u][2 * q + 1] << 32) | v[u][2 * q]);
-                  nan |= (f != f);
-                }
+            for (int u = 0; u < TILE_LOADS; ++u)
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const double f = __longlong_as_double(((long long)v[u][2 * q + 1] << 32) | v[u][2 * q]);
+                nan |= (f != f);
               }
-            }
           }
           if (nan) s_nan[(tb - tb_begin) & 1] = 1;
         }
 #pragma unroll
         for (int u = 0; u < TILE_LOADS; ++u) {
           const int g = g0 + 8 * NSUB * u;
-          if (off[u] >= 0 && !(a.dbg & 2)) {
+          if (g < n_units && !(a.dbg & 2)) {
             // unit g covers cells [g*CPU, g*CPU + CPU) of the [input][cell] row space
             TIN* sd = sx + (size_t)g * CPU * S;
             if constexpr (sizeof(TIN) == 4) {
