@@ -56,7 +56,7 @@ struct AggArgs {
   int n_tb;         // time blocks: ceil(T / 32)
   int chunk_tb;     // time blocks per work unit (a CTA keeps one bundle for a whole unit)
   int* work_counter; // device counter for dynamic unit scheduling (zeroed per launch)
-  int dbg;          // CTB_DEBUG bits (perf experiments): 1 skip loads, 2 skip STS, 4 skip gather
+  int dbg;          // CTB_DEBUG bits (perf experiments): 1 skip loads, 2 skip STS, 4 skip gather, 16 role split
   const int32_t *row_ptr, *col;
   const double* w;
   const int32_t *split_region, *split_slot_ptr;
@@ -156,6 +156,8 @@ agg_fused_kernel(const AggArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* const s_blob = smem_raw + a.tile_stride;
+  // experiment (CTB_DEBUG bit 16): first resident CTA of an SM only loads, the second only reduces
+  const int dbg = (a.dbg & 16) ? ((blockIdx.x < gridDim.x / 2) ? 6 : 1) : a.dbg;
   if (tid == 0) mbar_init(&s_bar, 1);
 
   // Work unit = (bundle, chunk of `chunk_tb` consecutive 32-day blocks), handed out by an
@@ -196,7 +198,7 @@ agg_fused_kernel(const AggArgs a) {
     const int t = t0 + dl;
     const int nPH = nP * HALVES;
     const int n_units = nPH * NIN;                 // unit index: [input][piece][half]
-    if (t < a.T && !(a.dbg & 1)) {
+    if (t < a.T && !(dbg & 1)) {
       const int64_t tp = a.tix ? a.tix[t] : t;
       const TIN* p0 = reinterpret_cast<const TIN*>(a.x0) + tp * a.stride;
       const TIN* p1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) + tp * a.stride : p0;
@@ -271,7 +273,7 @@ agg_fused_kernel(const AggArgs a) {
 #pragma unroll
         for (int u = 0; u < TILE_LOADS; ++u) {
           const int g = g0 + 8 * NSUB * u;
-          if (g < n_units && !(a.dbg & 2)) {
+          if (g < n_units && !(dbg & 2)) {
             // unit g covers cells [g*CPU, g*CPU + CPU) of the [input][cell] row space
             TIN* sd = sx + (size_t)g * CPU * S;
             if constexpr (sizeof(TIN) == 4) {
@@ -301,7 +303,7 @@ agg_fused_kernel(const AggArgs a) {
   const bool tile_nan = s_nan[(tb - tb_begin) & 1] != 0;
   if (tid == 0) s_nan[(tb - tb_begin + 1) & 1] = 0;   // flag of the next tile (nobody reads it now)
   // segments are sorted longest-first: round-robin over the warps is balanced
-  for (int s = warp; s < ((a.dbg & 4) ? 0 : H.n_seg); s += (THREADS / 32)) {
+  for (int s = warp; s < ((dbg & 4) ? 0 : H.n_seg); s += (THREADS / 32)) {
     const CtbSeg sg = segs[s];
     double acc[NOUT], acc2[NOUT];
 #pragma unroll
@@ -382,7 +384,7 @@ agg_fused_kernel(const AggArgs a) {
       if (sg.target >= 0) {
 #pragma unroll
         for (int j = 0; j < NOUT; ++j)
-          a.out[((size_t)j * a.R + sg.target) * a.out_ld + t] = (acc[j] + acc2[j]) * sg.rden;
+          __stcs(&a.out[((size_t)j * a.R + sg.target) * a.out_ld + t], (acc[j] + acc2[j]) * sg.rden);   // written once: leave L2 to the input
       } else {
         const int slot_o = ~sg.target;
 #pragma unroll
@@ -464,7 +466,8 @@ int launch_staged(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
   int n_sm = 0;
   CTB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device));
   const int by_smem = (int)((164 * 1024) / (smem + 1024 + 64));
-  const int ctas_per_sm = std::max(1, std::min(THREADS >= 1024 ? 1 : 2, by_smem));
+  int ctas_per_sm = std::max(1, std::min(THREADS >= 1024 ? 1 : 2, by_smem));
+  if (const char* e = getenv("CTB_CTAS")) ctas_per_sm = std::max(1, std::min(ctas_per_sm, atoi(e)));   // experiments
   const int n_tb = (a.T + CTB_TB - 1) / CTB_TB;
   int chunk_tb = 4;
   if (const char* e = getenv("CTB_CHUNK_TB")) chunk_tb = std::max(1, atoi(e));
