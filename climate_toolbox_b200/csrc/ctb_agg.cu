@@ -145,7 +145,7 @@ template <typename TIN, int KIND, int NOUT, bool VEC, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 1024 ? 1 : 2))
 agg_fused_kernel(const AggArgs a) {
   constexpr int NIN = NIn<KIND>::v;
-  constexpr int TILE_LOADS = 8;
+  constexpr int TILE_LOADS = THREADS >= 512 ? 4 : 8;   // loads per thread in flight; 4 suffice with 32 loading warps per SM
   constexpr int S = CTB_S;
   constexpr int HALVES = sizeof(TIN) / 4;       // 16-byte units per piece-day of one input
   constexpr int CPU = 16 / sizeof(TIN);          // cells per unit
