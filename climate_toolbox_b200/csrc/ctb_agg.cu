@@ -247,17 +247,19 @@ agg_fused_kernel(const AggArgs a) {
           }
         }
         if constexpr (KIND == CTB_TR_IDENTITY) {
+          // any NaN or infinity among the staged values?  (the fast reduction below multiplies
+          // padding entries of weight 0 into real cells: exact only for finite data)
           bool nan;
           if constexpr (sizeof(TIN) == 4) {
-            // NaN-propagating 3-input max over the 32 staged values: 16 instructions
-            float m = __uint_as_float(v[0][0]);
+            // NaN-propagating 3-input max of the magnitudes: two instructions per load
+            float m = 0.f;
 #pragma unroll
             for (int u = 0; u < TILE_LOADS; ++u)
 #pragma unroll
               for (int q = 0; q < 4; q += 2)
                 asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(m)
-                    : "f"(__uint_as_float(v[u][q])), "f"(__uint_as_float(v[u][q + 1])));
-            nan = (m != m);
+                    : "f"(fabsf(__uint_as_float(v[u][q]))), "f"(fabsf(__uint_as_float(v[u][q + 1]))));
+            nan = !(m <= 3.402823466e38f);
           } else {
             nan = false;
 #pragma unroll
@@ -265,7 +267,7 @@ agg_fused_kernel(const AggArgs a) {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const double f = __longlong_as_double(((long long)v[u][2 * q + 1] << 32) | v[u][2 * q]);
-                nan |= (f != f);
+                nan |= !(fabs(f) <= 1.7976931348623157e308);
               }
           }
           if (nan) s_nan[(tb - tb_begin) & 1] = 1;
@@ -375,7 +377,24 @@ agg_fused_kernel(const AggArgs a) {
           accumulate<TIN, KIND, NOUT, CHECK>(a.tr, W[e], at0(OFF[e]), TIN(0), acc);
       };
       if constexpr (KIND == CTB_TR_IDENTITY) {
-        if (tile_nan) body(std::true_type{}); else body(std::false_type{});
+        if (tile_nan) {
+          body(std::true_type{});
+        } else {
+          // all staged values are finite: run the entry range padded to a multiple of 4 (the
+          // padding has weight 0 and points at cell 0), no ragged tail, no per-value check
+          const int e_pad = e0 + (((int)sg.n + 3) & ~3);
+#pragma unroll 2
+          for (int e = e0; e < e_pad; e += 4) {
+            const uint4 o = *reinterpret_cast<const uint4*>(OFF + e);
+            const double2 w01 = *reinterpret_cast<const double2*>(W + e);
+            const double2 w23 = *reinterpret_cast<const double2*>(W + e + 2);
+            const TIN x0 = at0(o.x), x1 = at0(o.y), x2 = at0(o.z), x3 = at0(o.w);
+            acc[0] = fma(w01.x, (double)x0, acc[0]);
+            acc2[0] = fma(w01.y, (double)x1, acc2[0]);
+            acc[0] = fma(w23.x, (double)x2, acc[0]);
+            acc2[0] = fma(w23.y, (double)x3, acc2[0]);
+          }
+        }
       } else {
         body(std::true_type{});   // polynomials: one code path (two measured slower)
       }

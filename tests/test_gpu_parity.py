@@ -218,6 +218,30 @@ def test_quarter_degree_sample_vs_oracle(aggwt, agglev):
         check(out.tas.values, ref, scale)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_infinite_and_nan_values_take_the_checked_reduction(dtype):
+    """The fused kernel reduces tiles of finite values without per-value checks (and with the
+    entry ranges padded by zero-weight entries); a tile that staged a NaN or an infinity must
+    take the checked path: +inf / -inf propagate, inf - inf = NaN, NaN products are skipped."""
+    lat, lon, df, tas, _, _ = _config(1.0, 800, 40, nan_frac=0.0, dtype=dtype)
+    ii, jj = np.searchsorted(lat, df.lat.values), np.searchsorted(lon, df.lon.values)
+    big = df.groupby("hierid").size().sort_values().index[-3:]        # three multi-cell regions
+    rows = [np.flatnonzero(df.hierid.values == r) for r in big]
+    tas[3, ii[rows[0][0]], jj[rows[0][0]]] = np.inf                     # +inf alone
+    tas[7, ii[rows[1][0]], jj[rows[1][0]]] = np.inf                     # +inf and -inf in one region-day
+    k = next(q for q in rows[1] if (ii[q], jj[q]) != (ii[rows[1][0]], jj[rows[1][0]]))
+    tas[7, ii[k], jj[k]] = -np.inf
+    tas[33, ii[rows[2][0]], jj[rows[2][0]]] = np.nan                    # NaN next to -inf
+    tas[33, ii[rows[2][-1]], jj[rows[2][-1]]] = -np.inf
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": np.arange(40), "lat": lat, "lon": lon})
+    ref = oracle.weighted_aggregate_grid_to_regions(tas, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")[0]
+    assert np.isinf(ref).any() and np.isnan(ref).any()
+    for variant in (N.VARIANT_STAGED, N.VARIANT_DIRECT):
+        out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=df, variant=variant)
+        check(out.tas.values, ref, tol=1e-9)
+
+
 def test_lon_0_360_and_leap_day_folded_into_the_kernel():
     lat, lon360, df, tas, _, _ = _config(1.0, 800, 45, lon_0_360=True)
     time = pd.date_range("2000-02-01", periods=45)
