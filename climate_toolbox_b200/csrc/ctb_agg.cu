@@ -116,6 +116,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// shared-memory load by 32-bit shared-window address
+template <typename T>
+__device__ __forceinline__ T lds_val(uint32_t addr) {
+  T v;
+  if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // one CSR entry: acc_j += w * f_j(x), NaN products skipped (skipna sum, aggregations.py:78).
 // CHECK = false: the tile was seen to hold no NaN while it was staged (IDENTITY / POLY only,
 // where f is NaN iff x is).
@@ -297,11 +306,12 @@ agg_fused_kernel(const AggArgs a) {
   const CtbSeg* segs = reinterpret_cast<const CtbSeg*>(mb + H.off_seg);
   const double* W = reinterpret_cast<const double*>(mb + H.off_w);
   const uint32_t* OFF = reinterpret_cast<const uint32_t*>(mb + H.off_loc);   // byte offsets of staged cells
-  const unsigned char* sb0 = smem_raw + lane * sizeof(TIN);
-  const unsigned char* sb1 = sb0 + (size_t)nP * CTB_PIECE * S * sizeof(TIN);
+  // 32-bit shared-window addresses: one add per staged value (generic pointers cost two)
+  const uint32_t sb0 = smem_u32(smem_raw) + lane * (uint32_t)sizeof(TIN);
+  const uint32_t sb1 = sb0 + (uint32_t)(nP * CTB_PIECE * S) * (uint32_t)sizeof(TIN);
   const int t = t0 + lane;
-  auto at0 = [&](uint32_t o) { return *reinterpret_cast<const TIN*>(sb0 + o); };
-  auto at1 = [&](uint32_t o) { return *reinterpret_cast<const TIN*>(sb1 + o); };
+  auto at0 = [&](uint32_t o) { return lds_val<TIN>(sb0 + o); };
+  auto at1 = [&](uint32_t o) { return lds_val<TIN>(sb1 + o); };
   const bool tile_nan = s_nan[(tb - tb_begin) & 1] != 0;
   if (tid == 0) s_nan[(tb - tb_begin + 1) & 1] = 0;   // flag of the next tile (nobody reads it now)
   // segments are sorted longest-first: round-robin over the warps is balanced
