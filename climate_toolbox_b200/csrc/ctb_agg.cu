@@ -162,6 +162,7 @@ agg_fused_kernel(const AggArgs a) {
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_unit;
   __shared__ int s_nan[2];   // a NaN was staged into the tile (by tile parity)
+  __shared__ int s_seg_next;  // Snyder transforms: next region of the tile nobody has taken yet
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* const s_blob = smem_raw + a.tile_stride;
@@ -198,6 +199,7 @@ agg_fused_kernel(const AggArgs a) {
   for (int tb = tb_begin; tb < tb_end; ++tb) {
   const int t0 = tb * CTB_TB;
   if (tb != tb_begin) __syncthreads();   // tile buffer free again
+  if (tid == 0) s_seg_next = 0;
   // ---------------- stage: [day][piece] global  ->  [input][cell][day] shared -------------
   {
     const int l8 = lane & 7, l4 = lane >> 3;
@@ -315,7 +317,12 @@ agg_fused_kernel(const AggArgs a) {
   const bool tile_nan = s_nan[(tb - tb_begin) & 1] != 0;
   if (tid == 0) s_nan[(tb - tb_begin + 1) & 1] = 0;   // flag of the next tile (nobody reads it now)
   // segments are sorted longest-first: round-robin over the warps is balanced
-  for (int s = warp; s < ((dbg & 4) ? 0 : H.n_seg); s += (THREADS / 32)) {
+  // Snyder transforms: the reduction of a region costs thousands of cycles, so warps take the
+  // next region from a shared counter (list scheduling of the longest-first order) instead of
+  // a fixed round-robin share; for the cheap transforms the atomic is not worth it.
+  constexpr bool DYN_SEGS = (KIND == CTB_TR_EDD || KIND == CTB_TR_GDD);
+  const int n_seg_run = (dbg & 4) ? 0 : H.n_seg;
+  for (int s = warp; s < n_seg_run;) {
     const CtbSeg sg = segs[s];
     double acc[NOUT], acc2[NOUT];
 #pragma unroll
@@ -420,6 +427,13 @@ agg_fused_kernel(const AggArgs a) {
         for (int j = 0; j < NOUT; ++j)
           a.scratch[((size_t)j * a.n_scratch + slot_o) * a.T + t] = acc[j] + acc2[j];
       }
+    }
+    if constexpr (DYN_SEGS) {
+      int nx = 0;
+      if (lane == 0) nx = (THREADS / 32) + atomicAdd(&s_seg_next, 1);
+      s = __shfl_sync(0xffffffffu, nx, 0);
+    } else {
+      s += THREADS / 32;
     }
   }
   }   // tiles of the unit

@@ -143,9 +143,15 @@ __device__ __forceinline__ double ctb_ipow(double d, int p) {
 // one sqrt.  `rW` = 1/W is shared by all thresholds of a gridcell-day.
 #include "ctb_edd_coeffs.h"
 
+// The coefficients live in constant memory so that every DFMA takes its coefficient as a
+// constant-bank operand; as literals each one costs two UMOVs per evaluation (half of the
+// instructions of the Snyder kernels).
+static __constant__ double ctb_edd_A[CTB_EDD_A_N] = CTB_EDD_A_COEFFS;
+static __constant__ double ctb_edd_B[CTB_EDD_B_N] = CTB_EDD_B_COEFFS;
+
 __device__ __forceinline__ double ctb_edd_g(double a) {
-  constexpr double A[CTB_EDD_A_N] = CTB_EDD_A_COEFFS;
-  constexpr double B[CTB_EDD_B_N] = CTB_EDD_B_COEFFS;
+  const double* const A = ctb_edd_A;
+  const double* const B = ctb_edd_B;
   const double v = 1.0 - a;
   const double ta = fma(4.0, a, -1.0), tb = fma(4.0, v, -1.0);
   double pa = A[CTB_EDD_A_N - 1], pb = B[CTB_EDD_B_N - 1];
