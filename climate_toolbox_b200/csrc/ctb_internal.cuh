@@ -136,30 +136,26 @@ __device__ __forceinline__ double ctb_ipow(double d, int p) {
 //                    = W * g(s),  g(s) = (sqrt(1-s^2) - s*acos(s)) / pi,  g(-a) = g(a) + a
 //   tmax <= e       :  0          (also when tmax is NaN)
 //   tmin >= e       :  M - e      (NaN when tmin is NaN)
-// g is evaluated by two degree-17 polynomials fitted to 80-bit reference values
-// (ctb_edd_coeffs.h, gen_edd_coeffs.py): a <= 1/2 directly, a > 1/2 after factoring the
-// (1-a)^(3/2) behaviour at the end point.  Against asin/cos in numpy the scheme agrees to
-// 4e-16 * max(|EDD|, W); it replaces an fp64 asin, a sqrt and two divisions by ~36 FMAs and
-// one sqrt.  `rW` = 1/W is shared by all thresholds of a gridcell-day.
+// g(a) = v^(3/2) * H(v), v = 1 - a: after factoring the (1-a)^(3/2) behaviour at the end point
+// the rest is analytic on [0, 1] (nearest singularity at v = 2), and ONE degree-16 polynomial
+// fitted to 80-bit reference values (ctb_edd_coeffs.h, gen_edd_coeffs.py) covers the whole
+// range.  Against asin/cos in numpy the scheme agrees to 4e-16 * max(|EDD|, W); it replaces an
+// fp64 asin, a sqrt and two divisions by 17 FMAs and one sqrt.  `rW` = 1/W is shared by all
+// thresholds of a gridcell-day.
 #include "ctb_edd_coeffs.h"
 
 // The coefficients live in constant memory so that every DFMA takes its coefficient as a
-// constant-bank operand; as literals each one costs two UMOVs per evaluation (half of the
-// instructions of the Snyder kernels).
-static __constant__ double ctb_edd_A[CTB_EDD_A_N] = CTB_EDD_A_COEFFS;
-static __constant__ double ctb_edd_B[CTB_EDD_B_N] = CTB_EDD_B_COEFFS;
+// constant-bank / uniform-register operand; as literals each one costs two UMOVs per evaluation
+// (half of the instructions of the Snyder kernels).
+static __constant__ double ctb_edd_H[CTB_EDD_H_N] = CTB_EDD_H_COEFFS;
 
-__device__ __forceinline__ double ctb_edd_g(double a) {
-  const double* const A = ctb_edd_A;
-  const double* const B = ctb_edd_B;
+__device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
   const double v = 1.0 - a;
-  const double ta = fma(4.0, a, -1.0), tb = fma(4.0, v, -1.0);
-  double pa = A[CTB_EDD_A_N - 1], pb = B[CTB_EDD_B_N - 1];
+  const double t = fma(2.0, v, -1.0);
+  double p = ctb_edd_H[CTB_EDD_H_N - 1];
 #pragma unroll
-  for (int k = CTB_EDD_A_N - 2; k >= 0; --k) pa = fma(pa, ta, A[k]);
-#pragma unroll
-  for (int k = CTB_EDD_B_N - 2; k >= 0; --k) pb = fma(pb, tb, B[k]);
-  return a <= 0.5 ? pa : v * sqrt(v) * pb;
+  for (int k = CTB_EDD_H_N - 2; k >= 0; --k) p = fma(p, t, ctb_edd_H[k]);
+  return v * sqrt(v) * p;
 }
 
 __device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double rW,
