@@ -14,14 +14,15 @@ src = torch.empty((T, len(lat) * len(lon)), dtype=torch.float32, pin_memory=True
 src.normal_()
 dst = torch.empty((T, w), dtype=torch.float32, pin_memory=True)
 print("packed cells", w, "of", src.shape[1], "cpus", os.cpu_count(), "runs per plane ~", "n/a")
-for th in (1, 2, 4, 8, 16, 32, 0):
+for nt, th in [(n, t) for t in (1, 4, 8, 16, 0) for n in ("1", "0")] * 2:
+    os.environ["CTB_PACK_NT"] = nt     # 1: streaming whole-line stores (default), 0: memcpy
     best = 1e9
     for rep in range(3):
         t = time.perf_counter()
         N.check(N.lib().ctb_host_pack(plan._h, C.c_void_p(src.data_ptr()), N.F32, src.shape[1], None, 0, T,
                                       C.c_void_p(dst.data_ptr()), th))
         best = min(best, time.perf_counter() - t)
-    print("threads %2d: %.1f ms  %.1f GB/s packed" % (th, best * 1e3, T * w * 4 / best / 1e9), flush=True)
+    print("nt=%s threads %2d: %.1f ms  %.1f GB/s packed" % (nt, th, best * 1e3, T * w * 4 / best / 1e9), flush=True)
 # plain big memcpy for reference
 a = np.empty(T * w, dtype=np.float32); b = np.empty_like(a)
 t = time.perf_counter(); b[:] = a; dt = time.perf_counter() - t

@@ -12,6 +12,10 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <numeric>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include "ctb_internal.cuh"
 
 // ------------------------------------------------------------ error state ---
@@ -417,17 +421,25 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
     for (int32_t c : col) cp.push_back(c / CTB_PIECE);
     std::sort(cp.begin(), cp.end());
     cp.erase(std::unique(cp.begin(), cp.end()), cp.end());
-    for (auto& c : col) {
-      const int32_t rank = (int32_t)(std::lower_bound(cp.begin(), cp.end(), c / CTB_PIECE) - cp.begin());
-      c = rank * CTB_PIECE + c % CTB_PIECE;
-    }
+    // every run of consecutive pieces starts on a 64-byte boundary of the packed plane (4 pieces
+    // of f32), so that ctb_host_pack can write whole cache lines with streaming stores
+    std::vector<int32_t> packed_of(cp.size());
+    int32_t cur = 0;
     for (size_t q = 0; q < cp.size();) {
       size_t e = q + 1;
       while (e < cp.size() && cp[e] == cp[e - 1] + 1) ++e;
-      P->h_pack_runs.push_back({cp[q], (int32_t)(e - q), (int32_t)q});
+      cur = (cur + 3) & ~3;
+      P->h_pack_runs.push_back({cp[q], (int32_t)(e - q), cur});
+      for (size_t k = q; k < e; ++k) packed_of[k] = cur + (int32_t)(k - q);
+      cur += (int32_t)(e - q);
       q = e;
     }
-    plan_ncell = (int64_t)cp.size() * CTB_PIECE;
+    cur = (cur + 3) & ~3;
+    for (auto& c : col) {
+      const size_t k = (size_t)(std::lower_bound(cp.begin(), cp.end(), c / CTB_PIECE) - cp.begin());
+      c = packed_of[k] * CTB_PIECE + c % CTB_PIECE;
+    }
+    plan_ncell = (int64_t)cur * CTB_PIECE;
     P->ncell = plan_ncell;   // what the kernels index
   }
 
@@ -659,15 +671,36 @@ extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_
   n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(T, 1));
   const char* src = static_cast<const char*>(x);
   char* out = static_cast<char*>(dst);
+  const bool nt = (reinterpret_cast<uintptr_t>(dst) & 63) == 0 && ((size_t)packed * es) % 64 == 0 &&
+                  !(getenv("CTB_PACK_NT") && atoi(getenv("CTB_PACK_NT")) == 0);
   auto work = [&](int64_t d0, int64_t d1) {
     for (int64_t d = d0; d < d1; ++d) {
       const int64_t tp = time_index ? time_index[t_begin + d] : t_begin + d;
       const char* plane = src + (size_t)tp * stride * es;
       char* o = out + (size_t)d * packed * es;
-      for (const auto& r : P->h_pack_runs)
-        std::memcpy(o + (size_t)r.packed_piece * piece_bytes, plane + (size_t)r.phys_piece * piece_bytes,
-                    (size_t)r.n_pieces * piece_bytes);
+      for (const auto& r : P->h_pack_runs) {
+        char* q = o + (size_t)r.packed_piece * piece_bytes;
+        const char* s = plane + (size_t)r.phys_piece * piece_bytes;
+        const size_t n = (size_t)r.n_pieces * piece_bytes;
+#if defined(__SSE2__)
+        if (nt) {
+          // runs start on 64-byte boundaries of the packed plane: write whole lines (the run, then
+          // zeros up to the next boundary) with streaming stores -- no read-for-ownership of the
+          // destination, which only the DMA engine will read
+          size_t i = 0;
+          for (; i < n; i += 16)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(q + i),
+                             _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i)));
+          for (; i & 63; i += 16) _mm_stream_si128(reinterpret_cast<__m128i*>(q + i), _mm_setzero_si128());
+          continue;
+        }
+#endif
+        std::memcpy(q, s, n);
+      }
     }
+#if defined(__SSE2__)
+    if (nt) _mm_sfence();
+#endif
   };
   if (n_threads == 1) { work(0, T); return CTB_OK; }
   std::vector<std::thread> pool;
