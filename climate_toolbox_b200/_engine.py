@@ -265,6 +265,41 @@ _PINNED = {}   # (slot, k) -> pinned staging tensor for packed chunks (reused ac
 TRANSFER_BYTES = {"h2d": 0, "d2h": 0}   # bytes actually copied across PCIe by this module (bench e2e)
 
 
+# ---------------------------------------------------------------------------
+# pinned result buffers
+# ---------------------------------------------------------------------------
+# Results go back to the host through pinned memory (a pageable D2H runs at 2 GB/s).  A fresh
+# cudaHostAlloc of a 285 MB block costs 200-400 ms, and torch's caching host allocator hands out a new
+# block whenever the previous one is not provably idle -- so the blocks are pooled here and return to
+# the pool when the last numpy view of a result is garbage collected.
+_RESULT_POOL = {}
+
+
+class _PinnedOwner:
+    """Base object of a result array: exposes a pinned block through __array_interface__."""
+
+    def __init__(self, block, shape, typestr):
+        self.__array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr,
+                                    "data": (block.data_ptr(), False), "version": 3}
+
+
+def _release_result(block):
+    _RESULT_POOL.setdefault(block.numel(), []).append(block)
+
+
+def pinned_result_like(t):
+    """(torch view, numpy array) over a pooled pinned block shaped like the CUDA tensor ``t``."""
+    import weakref
+    nbytes = max(1, t.numel() * t.element_size())
+    free = _RESULT_POOL.setdefault(nbytes, [])
+    block = free.pop() if free else torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    view = block[: t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+    owner = _PinnedOwner(block, t.shape, np.dtype(str(t.dtype).replace("torch.", "")).str)
+    arr = np.asarray(owner)
+    weakref.finalize(owner, _release_result, block)
+    return view, arr
+
+
 def _pinned_buffer(key, nbytes):
     b = _PINNED.get(key)
     if b is None or b.numel() < nbytes:
@@ -274,7 +309,7 @@ def _pinned_buffer(key, nbytes):
 
 
 def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(), n_out=1,
-                   variant=N.VARIANT_AUTO, chunk_bytes=96 << 20, zero_copy=None, threads=0):
+                   variant=N.VARIANT_AUTO, chunk_bytes=192 << 20, zero_copy=None, threads=0):
     """Host (numpy) inputs -> CUDA tensor [n_out, R, T].
 
     ``xs``: list of 1 or 2 C-contiguous numpy arrays viewed as 2-D

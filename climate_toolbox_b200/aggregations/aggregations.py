@@ -189,13 +189,12 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
             res = out
         else:
             # D2H into pinned memory (57 GB/s on the round-1 box; a pageable copy runs at
-            # 2 GB/s).  The block comes from torch's caching host allocator and is owned by
-            # the returned arrays.
-            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            # 2 GB/s).  The block comes from a pool and returns to it when the last view of
+            # the returned arrays is garbage collected.
+            host, res = E.pinned_result_like(out)
             host.copy_(out, non_blocking=True)
             E.TRANSFER_BYTES["d2h"] += out.numel() * out.element_size()
             torch.cuda.current_stream(out.device).synchronize()
-            res = host.numpy()
         R = plan.R
         for j, name in enumerate(g["names"]):
             a = res[j].reshape((R,) + v0.other_shape)      # (agglev, *others) in view order

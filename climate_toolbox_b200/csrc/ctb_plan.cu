@@ -654,6 +654,7 @@ extern "C" int ctb_plan_row_weights(const ctb_plan* plan, double* out) {
 }
 
 // ---------------------------------------------------------------- host ingest ---
+#include <atomic>
 #include <thread>
 
 extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_t stride,
@@ -703,12 +704,15 @@ extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_
 #endif
   };
   if (n_threads == 1) { work(0, T); return CTB_OK; }
+  // days are handed out one at a time: on a shared host a preempted core delays one day, not a
+  // whole static share of the chunk
+  std::atomic<int64_t> next{0};
+  auto loop = [&]() {
+    for (int64_t d; (d = next.fetch_add(1, std::memory_order_relaxed)) < T;) work(d, d + 1);
+  };
   std::vector<std::thread> pool;
-  const int64_t per = (T + n_threads - 1) / n_threads;
-  for (int i = 0; i < n_threads; ++i) {
-    const int64_t d0 = i * per, d1 = std::min<int64_t>(T, d0 + per);
-    if (d0 < d1) pool.emplace_back(work, d0, d1);
-  }
+  for (int i = 1; i < n_threads; ++i) pool.emplace_back(loop);
+  loop();   // the calling thread packs too
   for (auto& th : pool) th.join();
   return CTB_OK;
 }
