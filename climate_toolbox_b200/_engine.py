@@ -127,6 +127,13 @@ _PLAN_CACHE_SIZE = 8
 _PLAN_FAST = {}   # fingerprint of (DataFrame object, columns, grid) -> content key
 
 
+def _bitsum(a):
+    """Cheap order-insensitive fingerprint of a float column: sum of the raw 64-bit patterns
+    (mod 2^64) -- 10x faster than a nansum, and NaN payloads count too."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return int(a.view(np.uint64).sum(dtype=np.uint64))
+
+
 def region_codes(labels):
     """Sorted-unique region labels and the code of every row (NaN label -> -1);
     ``xarray.groupby`` orders groups like ``pd.factorize(sort=True)``."""
@@ -151,8 +158,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
         with np.errstate(all="ignore"):
             fp = (id(weights), len(weights), aggwt, agglev, backup_aggwt, stage_bytes, smem_budget,
                   bool(compact), int(elem_bytes), str(device), gh.hexdigest(),
-                  tuple(float(np.nansum(np.asarray(weights[c].values, dtype=np.float64)))
-                        for c in ("lat", "lon", aggwt, backup_aggwt)),
+                  tuple(_bitsum(weights[c].values) for c in ("lat", "lon", aggwt, backup_aggwt)),
                   str(weights[agglev].values[0]) if len(weights) else "",
                   str(weights[agglev].values[-1]) if len(weights) else "")
         hit = _PLAN_FAST.get(fp)
