@@ -142,7 +142,7 @@ def region_codes(labels):
 
 
 def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4, device=None,
-             smem_budget=0, cache=True, compact=False, elem_bytes=4):
+             smem_budget=0, cache=True, compact=False, elem_bytes=4, trusted=False):
     """Build (or fetch) the device plan for (grid, weights[lat, lon, agglev, aggwt, backup])."""
     device = device or default_device()
     for col in ("lat", "lon", agglev, aggwt, backup_aggwt):
@@ -158,7 +158,8 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
         with np.errstate(all="ignore"):
             fp = (id(weights), len(weights), aggwt, agglev, backup_aggwt, stage_bytes, smem_budget,
                   bool(compact), int(elem_bytes), str(device), gh.hexdigest(),
-                  tuple(_bitsum(weights[c].values) for c in ("lat", "lon", aggwt, backup_aggwt)),
+                  # `trusted`: a private frame of the caller (never edited in place): identity is enough
+                  () if trusted else tuple(_bitsum(weights[c].values) for c in ("lat", "lon", aggwt, backup_aggwt)),
                   str(weights[agglev].values[0]) if len(weights) else "",
                   str(weights[agglev].values[-1]) if len(weights) else "")
         hit = _PLAN_FAST.get(fp)

@@ -155,7 +155,7 @@ def _group_requests(reqs):
 
 
 def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant=N.VARIANT_AUTO,
-                    device=None, smem_budget=0, keep_on_device=False, pack_host=True):
+                    device=None, smem_budget=0, keep_on_device=False, pack_host=True, trusted_weights=False):
     lat, lon = _coord_labels(ds, "lat"), _coord_labels(ds, "lon")
     reqs = []
     for name in variables:
@@ -178,7 +178,8 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
         compact = (not v0.on_device) and v0.layout == N.LAYOUT_TIME_MAJOR and pack_host
         plan = E.get_plan(grid, weights, aggwt, agglev, backup_aggwt,
                           stage_bytes=len(views) * v0.elem_bytes, device=dev,
-                          smem_budget=smem_budget, compact=compact, elem_bytes=v0.elem_bytes)
+                          smem_budget=smem_budget, compact=compact, elem_bytes=v0.elem_bytes,
+                          trusted=trusted_weights)
         n_out = len(g["names"])
         out = _run_group(plan, views, g["kind"], g["params"], n_out, variant)  # [n_out, R, T]
         # reference dim order: agglev takes the place of the first of (lat, lon)
@@ -381,6 +382,77 @@ def weighted_aggregate_grid_to_regions(ds, variable, aggwt, agglev, weights=None
     names = [variable] if isinstance(variable, str) else list(variable)
     return to_like(_aggregate_core(ds, names, aggwt, agglev, weights, backup_aggwt,
                                    **engine_opts), like)
+
+
+_STACKED = {}   # (id(weights), columns) -> (weights ref, stacked frame): keeps the plan-cache fast path warm
+
+
+def weighted_aggregate_grid_to_regions_multi(ds, variable, aggwts, agglev, weights,
+                                             backup_aggwt="areawt", **engine_opts):
+    """
+    Extension: aggregate ``variable`` with SEVERAL weight columns in ONE pass over
+    the gridded data.  Equivalent to one ``weighted_aggregate_grid_to_regions`` call per entry of
+    ``aggwts`` (reference ``aggregations.py:87-124`` run once per weight), but the data is
+    staged once: every region is entered once per weight column as a "virtual" region
+    ``(k, region)``, the virtual regions of a region share their gridcell footprint and land in
+    the same kernel work bundle.
+
+    Returns a Dataset with one variable per weight column named ``"<variable>_<aggwt>"``.
+    """
+    if isinstance(weights, str):
+        weights = prepare_spatial_weights_data(weights)
+    aggwts = list(aggwts)
+    for col in ["lat", "lon", agglev, backup_aggwt] + aggwts:
+        if col not in weights:
+            raise KeyError(col)
+    if not isinstance(variable, str):
+        raise TypeError("weighted_aggregate_grid_to_regions_multi takes one variable name")
+    key = (id(weights), tuple(aggwts), agglev, backup_aggwt, len(weights))
+    hit = _STACKED.get(key)
+    sums = tuple(E._bitsum(weights[c].values) for c in aggwts + [backup_aggwt, "lat", "lon"])
+    if hit is not None and hit[0] is weights and hit[2] == sums:
+        stacked, labels, present = hit[1], hit[3], hit[4]
+    else:
+        codes, labels = E.region_codes(weights[agglev].values)
+        R = len(labels)
+        n = len(weights)
+        K = len(aggwts)
+        virt = np.concatenate([np.where(codes >= 0, codes.astype(np.int64) + k * R, -1) for k in range(K)])
+        stacked = pd.DataFrame({
+            "lat": np.tile(np.asarray(weights["lat"].values, dtype=np.float64), K),
+            "lon": np.tile(np.asarray(weights["lon"].values, dtype=np.float64), K),
+            "_lev": np.where(virt >= 0, virt, np.nan),      # NaN labels are dropped, as in the reference
+            "_w": np.concatenate([np.asarray(weights[c].values, dtype=np.float64) for c in aggwts]),
+            "_bk": np.tile(np.asarray(weights[backup_aggwt].values, dtype=np.float64), K)})
+        present = np.unique(virt[virt >= 0])               # virtual regions that have rows, in plan order
+        if len(_STACKED) > 8:
+            _STACKED.clear()
+        _STACKED[key] = (weights, stacked, sums, labels, present)
+    like = ds
+    ds = from_any(ds)
+    res = _aggregate_core(ds, [variable], "_w", "_lev", stacked, "_bk", trusted_weights=True, **engine_opts)
+    var = res._vars[variable]
+    ax = var.dims.index("_lev")
+    R, K = len(labels), len(aggwts)
+    out = Dataset()
+    dims = tuple(agglev if d == "_lev" else d for d in var.dims)
+    data = var.physical      # numpy (pinned block) or, with keep_on_device, the CUDA tensor itself
+    for k, w in enumerate(aggwts):
+        sel = np.flatnonzero((present >= k * R) & (present < (k + 1) * R))
+        if len(sel) and sel[-1] - sel[0] + 1 == len(sel):      # the usual case: a contiguous block -> a view
+            idx = [slice(None)] * len(var.dims)
+            idx[ax] = slice(int(sel[0]), int(sel[-1]) + 1)
+            a = data[tuple(idx)]
+        elif isinstance(data, torch.Tensor):
+            a = data.index_select(ax, torch.as_tensor(sel, device=data.device))
+        else:
+            a = np.take(data, sel, axis=ax)
+        out["{}_{}".format(variable, w)] = Variable(dims, a, var.attrs)
+    out._coords[agglev] = Variable((agglev,), np.asarray(labels))
+    for d, c in res._coords.items():
+        if d != "_lev":
+            out._coords[d] = c
+    return to_like(out, like)
 
 
 @functools.lru_cache(maxsize=8)

@@ -17,7 +17,7 @@ from climate_toolbox_b200 import _engine as E
 from climate_toolbox_b200 import _native as N
 from climate_toolbox_b200.aggregations.aggregations import (
     _aggregate_reindexed_data_to_regions, _reindex_spatial_data_to_regions,
-    weighted_aggregate_grid_to_regions)
+    weighted_aggregate_grid_to_regions, weighted_aggregate_grid_to_regions_multi)
 from climate_toolbox_b200.io import load_bcsd
 from climate_toolbox_b200.transformations.transformations import snyder_edd, snyder_gdd, tas_poly
 
@@ -242,6 +242,29 @@ def test_infinite_and_nan_values_take_the_checked_reduction(dtype):
     for variant in (N.VARIANT_STAGED, N.VARIANT_DIRECT):
         out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=df, variant=variant)
         check(out.tas.values, ref, tol=1e-9)
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_several_weight_columns_in_one_pass(where):
+    """popwt + areawt + cropwt from one pass over the data == three reference passes."""
+    lat, lon, df, tas, _, _ = _config(1.0, 1500, 45)
+    df = df.copy()
+    df.loc[df.index[::97], "hierid"] = np.nan            # rows without a region are dropped
+    data = tas if where == "host" else torch.from_numpy(tas).cuda()
+    ds = Dataset({"tas": (("time", "lat", "lon"), data)},
+                 coords={"time": np.arange(45), "lat": lat, "lon": lon})
+    cols = ["popwt", "areawt", "cropwt"]
+    n0 = E.launch_count()
+    E.get_plan  # noqa: B018
+    out = weighted_aggregate_grid_to_regions_multi(ds, "tas", cols, "hierid", df)
+    for c in cols:
+        ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, c, "hierid")
+        got = out["tas_" + c]
+        assert got.dims == rd and list(out.hierid.values) == list(labels)
+        check(got.values if where == "host" else got.values, ref, scale)
+    # and it is the same as three single calls
+    one = weighted_aggregate_grid_to_regions(ds, "tas", "cropwt", "hierid", weights=df)
+    np.testing.assert_allclose(out["tas_cropwt"].values, one.tas.values, rtol=1e-12, equal_nan=True)
 
 
 def test_results_own_their_pinned_blocks():
