@@ -13,14 +13,18 @@
 //           as ONE bulk async copy (cp.async.bulk, TMA 1-D) signalled on an mbarrier, once
 //           per unit;
 //   stage : 16-byte coalesced global loads of the footprint's 4-cell pieces for 32
-//           day-planes, 8 in flight per thread, written TRANSPOSED into smem as a cell-major
-//           tile sx[cell][day] (row stride 33 words => conflict-free both ways);
+//           day-planes, 4 in flight per thread, written TRANSPOSED into smem as a cell-major
+//           tile sx[cell][day] (row stride 33 words => conflict-free both ways); a 3-input
+//           NaN-propagating max of the magnitudes flags tiles that hold a NaN or infinity;
 //   gather: one warp per region, lane = day; per 4 CSR entries three vector LDS of
-//           metadata + four conflict-free LDS of data, fp64 FMA, NaN products skipped;
-//           out[r][t] = acc / den[r], 256-byte coalesced stores along time.
-// One CTA of an SM stages while the other gathers; only hardware barriers are used.
+//           metadata + four conflict-free LDS of data, fp64 FMA; finite tiles run the padded
+//           entry range without checks, flagged tiles skip NaN products one by one;
+//           out[r][t] = acc / den[r], 256-byte coalesced streaming stores along time.
+// Only hardware barriers separate the phases.  The phase times of the two resident CTAs add
+// up: a CTA with loads outstanding and a CTA reducing out of shared memory do not overlap on
+// one SM (role-split experiment), so each phase is kept short instead.
 // Shared memory is capped at 164 KB per SM: it is carved out of the L1, and the L1 that is
-// left bounds the loads in flight (bench_micro/stage_bw3.py: 4.2 -> 2.1 TB/s at 228 KB).
+// left holds the loads in flight (bench_micro/stage_bw3.py: 4.2 -> 2.1 TB/s at 228 KB).
 // Alternatives that were built and measured slower are described in DESIGN.md.
 // Direct kernel (CELL_MAJOR input [lat][lon][T], or any layout as a fallback):
 //   one warp per (region, 32-day tile), lane = day, coalesced along time.
