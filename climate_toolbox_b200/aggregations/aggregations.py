@@ -384,6 +384,22 @@ def weighted_aggregate_grid_to_regions(ds, variable, aggwt, agglev, weights=None
                                    **engine_opts), like)
 
 
+def _stack_weight_columns(weights, aggwts, agglev, backup_aggwt):
+    """One frame with a copy of the rows per weight column: region r under column k becomes the
+    virtual region ``k * R + code(r)``.  Returns (frame[lat, lon, _lev, _w, _bk], sorted region
+    labels, sorted virtual codes that have rows)."""
+    codes, labels = E.region_codes(weights[agglev].values)
+    R, K = len(labels), len(aggwts)
+    virt = np.concatenate([np.where(codes >= 0, codes.astype(np.int64) + k * R, -1) for k in range(K)])
+    stacked = pd.DataFrame({
+        "lat": np.tile(np.asarray(weights["lat"].values, dtype=np.float64), K),
+        "lon": np.tile(np.asarray(weights["lon"].values, dtype=np.float64), K),
+        "_lev": np.where(virt >= 0, virt, np.nan),      # NaN labels are dropped, as in the reference
+        "_w": np.concatenate([np.asarray(weights[c].values, dtype=np.float64) for c in aggwts]),
+        "_bk": np.tile(np.asarray(weights[backup_aggwt].values, dtype=np.float64), K)})
+    return stacked, labels, np.unique(virt[virt >= 0])
+
+
 _STACKED = {}   # (id(weights), columns) -> (weights ref, stacked frame): keeps the plan-cache fast path warm
 
 
@@ -413,18 +429,7 @@ def weighted_aggregate_grid_to_regions_multi(ds, variable, aggwts, agglev, weigh
     if hit is not None and hit[0] is weights and hit[2] == sums:
         stacked, labels, present = hit[1], hit[3], hit[4]
     else:
-        codes, labels = E.region_codes(weights[agglev].values)
-        R = len(labels)
-        n = len(weights)
-        K = len(aggwts)
-        virt = np.concatenate([np.where(codes >= 0, codes.astype(np.int64) + k * R, -1) for k in range(K)])
-        stacked = pd.DataFrame({
-            "lat": np.tile(np.asarray(weights["lat"].values, dtype=np.float64), K),
-            "lon": np.tile(np.asarray(weights["lon"].values, dtype=np.float64), K),
-            "_lev": np.where(virt >= 0, virt, np.nan),      # NaN labels are dropped, as in the reference
-            "_w": np.concatenate([np.asarray(weights[c].values, dtype=np.float64) for c in aggwts]),
-            "_bk": np.tile(np.asarray(weights[backup_aggwt].values, dtype=np.float64), K)})
-        present = np.unique(virt[virt >= 0])               # virtual regions that have rows, in plan order
+        stacked, labels, present = _stack_weight_columns(weights, aggwts, agglev, backup_aggwt)
         if len(_STACKED) > 8:
             _STACKED.clear()
         _STACKED[key] = (weights, stacked, sums, labels, present)

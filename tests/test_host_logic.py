@@ -164,3 +164,25 @@ def test_weights_none_is_typeerror_like_the_reference(clim_data):
     from climate_toolbox_b200.aggregations.aggregations import weighted_aggregate_grid_to_regions
     with pytest.raises(TypeError):
         weighted_aggregate_grid_to_regions(clim_data, "temperature", "popwt", "ISO")
+
+
+def test_stacked_weight_columns_for_one_pass_multi_weight():
+    """SURVEY 8-f2 host logic: K copies of the rows, virtual region k*R + code, NaN labels dropped;
+    aggregating the stacked frame with the oracle equals one oracle pass per column."""
+    import oracle
+    from climate_toolbox_b200 import synthetic
+    from climate_toolbox_b200.aggregations.aggregations import _stack_weight_columns
+    lat, lon = synthetic.grid_labels(5.0)
+    df = synthetic.weights_table(5.0, 40, seed=3).copy()
+    df.loc[df.index[::11], "hierid"] = np.nan
+    cols = ["popwt", "cropwt"]
+    st, labels, present = _stack_weight_columns(df, cols, "hierid", "areawt")
+    R = len(labels)
+    assert len(st) == 2 * len(df) and list(labels) == sorted(set(df.hierid.dropna()))
+    assert np.isnan(st["_lev"].values).sum() == 2 * df.hierid.isna().sum()
+    np.testing.assert_array_equal(present, np.arange(2 * R))
+    x = np.random.default_rng(0).normal(280, 10, (6, len(lat), len(lon)))
+    got = oracle.weighted_aggregate_grid_to_regions(x, ("time", "lat", "lon"), lat, lon, st, "_w", "_lev", "_bk")[0]
+    for k, c in enumerate(cols):
+        ref = oracle.weighted_aggregate_grid_to_regions(x, ("time", "lat", "lon"), lat, lon, df, c, "hierid")[0]
+        np.testing.assert_allclose(got[:, k * R:(k + 1) * R], ref, rtol=1e-13, equal_nan=True)
