@@ -70,3 +70,49 @@ def test_time_sharded_gather_world2(T):
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), res
+
+
+def _oracle_aggregate(ds, variable, aggwt, agglev, weights=None, backup_aggwt="areawt", **kw):
+    """Stand-in for the single-GPU aggregation (CPU tests have no GPU): the oracle behind the
+    public signature, returning this package's Dataset."""
+    import oracle
+    from climate_toolbox_b200 import Dataset
+    x = ds[variable].values
+    out, rd, labels = oracle.weighted_aggregate_grid_to_regions(
+        x, ds[variable].dims, ds["lat"].values, ds["lon"].values, weights, aggwt, agglev, backup_aggwt)
+    return Dataset({variable: (rd, out)}, coords={"time": ds["time"].values, agglev: labels})
+
+
+def _worker_api(rank, world, port, T, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from climate_toolbox_b200 import Dataset, synthetic
+        from climate_toolbox_b200.parallel import aggregate_time_sharded
+        lat, lon = synthetic.grid_labels(4.0)
+        df = synthetic.weights_table(4.0, 60, seed=2)
+        tas, _, _ = synthetic.tas_field(T, len(lat), len(lon), seed=1, dtype=np.float64)
+        ds = Dataset({"tas": (("time", "lat", "lon"), tas)}, coords={"time": np.arange(T), "lat": lat, "lon": lon})
+        full = aggregate_time_sharded(ds, "tas", "popwt", "hierid", df, aggregate_fn=_oracle_aggregate)
+        part = aggregate_time_sharded(ds, "tas", "popwt", "hierid", df, gather=False, aggregate_fn=_oracle_aggregate)
+        ref = oracle.weighted_aggregate_grid_to_regions(tas, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")[0]
+        ok = np.array_equal(full["tas"].values, ref, equal_nan=True) and full["tas"].dims == ("time", "hierid") \
+            and np.array_equal(full["time"].values, np.arange(T)) and part["tas"].shape[0] < T
+        q.put((rank, bool(ok), tuple(full["tas"].shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_aggregate_time_sharded_api_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_api, args=(r, 2, port, 70, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
