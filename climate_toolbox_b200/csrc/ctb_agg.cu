@@ -523,12 +523,12 @@ int launch_staged(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
   const int64_t n_units = (int64_t)P->n_bundles * n_chunks;
   if (n_units >= (1ll << 31)) { ctb_set_error("too many work units"); return CTB_ERR_UNSUPPORTED; }
   a.n_bundles = P->n_bundles; a.n_items = (int)n_units; a.n_tb = n_tb; a.chunk_tb = std::max(chunk_tb, 1);
-  a.tile_stride = (int)tile; a.meta_b_stride = 0; a.work_counter = P->d_work_counter;
+  a.tile_stride = (int)tile; a.meta_b_stride = 0; a.work_counter = P->d_work_counter + P->work_counter_slot.fetch_add(1) % CTB_N_WORK_COUNTERS;
   { const char* e = getenv("CTB_DEBUG"); a.dbg = e ? atoi(e) : 0; }
   if (n_units > 0) {
     const unsigned grid = (unsigned)std::min<int64_t>(n_units, (int64_t)n_sm * ctas_per_sm);
     const int carveout = (int)((ctas_per_sm * (smem + 1024 + 64) + 2048) * 100 / (228 * 1024)) + 1;
-    CTB_CUDA(cudaMemsetAsync(P->d_work_counter, 0, sizeof(int), st));
+    CTB_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
     if (vec) {
       auto k = agg_fused_kernel<TIN, KIND, NOUT, true, THREADS>;
       CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

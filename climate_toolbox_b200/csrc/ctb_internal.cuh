@@ -71,6 +71,7 @@ constexpr int CTB_CTAS_PER_SM = 2;
 constexpr int CTB_SMEM_PER_CTA = 164 * 1024 / CTB_CTAS_PER_SM - 1024 - 512;  // 82,432 B
 // metadata blob: part A (header + piece list) and part B (segment table + weights +
 // staged-cell indices) are contiguous in global memory and arrive as ONE bulk copy
+constexpr int CTB_N_WORK_COUNTERS = 64;
 constexpr int CTB_META_A_CAP = 32 + CTB_TILE_UNITS * 4;
 constexpr int CTB_META_B_CAP = (CTB_SMEM_PER_CTA - CTB_TILE_BYTES - CTB_META_A_CAP) & ~15;
 
@@ -92,8 +93,11 @@ struct ctb_plan {
   int32_t n_bundles = 0, n_segments = 0;
   int64_t* d_b_blob_off = nullptr;   // [n_bundles+1] byte offsets into d_blob (16 B aligned)
   int4* d_b_desc = nullptr;          // [n_bundles] {off_lo, off_hi, bytes_a, bytes_b}
-  int* d_work_counter = nullptr;     // dynamic unit scheduler of the fused kernel (zeroed per launch;
-                                     // concurrent launches on one plan must share a stream)
+  // dynamic unit scheduler of the fused kernel: CTB_N_WORK_COUNTERS device counters used round-robin,
+  // one per launch (zeroed on the launch's stream), so that launches of one plan on different
+  // streams do not share a counter
+  int* d_work_counter = nullptr;
+  mutable std::atomic<uint32_t> work_counter_slot{0};
   uint8_t* d_blob = nullptr;         // per-bundle metadata blobs, see CtbBlobHeader
   // regions split over several bundles: out[r] = sum(scratch[slot0..slot1)) / den[r]
   int32_t n_split = 0, n_scratch = 0;

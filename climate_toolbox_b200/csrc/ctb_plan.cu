@@ -579,7 +579,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   if ((rc = upload(&P->d_b_blob_off, B.b_blob_off))) return rc;
   if ((rc = upload(&P->d_blob, B.blob))) return rc;
   if ((rc = upload(&P->d_b_desc, B.desc))) return rc;
-  CTB_CUDA(cudaMalloc((void**)&P->d_work_counter, sizeof(int)));
+  CTB_CUDA(cudaMalloc((void**)&P->d_work_counter, CTB_N_WORK_COUNTERS * sizeof(int)));
   if ((rc = upload(&P->d_split_region, split_region))) return rc;
   if ((rc = upload(&P->d_split_slot_ptr, split_slot_ptr))) return rc;
   P->n_bundles = (int32_t)B.b_blob_off.size() - 1;

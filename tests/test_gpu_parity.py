@@ -267,6 +267,29 @@ def test_several_weight_columns_in_one_pass(where):
     np.testing.assert_allclose(out["tas_cropwt"].values, one.tas.values, rtol=1e-12, equal_nan=True)
 
 
+def test_one_plan_on_two_streams_at_once():
+    """Launches of one plan on different streams take different scheduler counters."""
+    lat, lon, df, tas, _, _ = _config(1.0, 3000, 365, nan_frac=0.0)
+    x = torch.from_numpy(tas).cuda().view(365, -1)
+    plan = E.get_plan(E.GridSpec(lat, lon), df, "popwt", "hierid")
+    ref = E.aggregate_device(plan, x, None, N.LAYOUT_TIME_MAJOR, x.shape[1], None, 365, "identity", (), 1,
+                             N.VARIANT_STAGED)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[torch.empty_like(ref) for _ in range(20)] for _ in streams]
+    wss = [torch.empty(max(1, N.lib().ctb_aggregate_workspace_bytes(plan._h, 365, 1) // 8), dtype=torch.float64,
+                       device="cuda") for _ in streams]
+    for i in range(20):
+        for s, o, ws in zip(streams, outs, wss):
+            with torch.cuda.stream(s):
+                E.aggregate_device(plan, x, None, N.LAYOUT_TIME_MAJOR, x.shape[1], None, 365, "identity", (), 1,
+                                   N.VARIANT_STAGED, out=o[i], workspace=ws)
+    torch.cuda.synchronize()
+    for o in outs:
+        for t in o:
+            assert torch.equal(t, ref)
+
+
 def test_results_own_their_pinned_blocks():
     """Host results come back in pooled pinned blocks: a block may be reused only after every view
     of the result it carried is gone."""
