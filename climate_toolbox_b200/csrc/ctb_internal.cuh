@@ -156,10 +156,16 @@ static __constant__ double ctb_edd_H[CTB_EDD_H_N] = CTB_EDD_H_COEFFS;
 __device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
   const double v = 1.0 - a;
   const double t = fma(2.0, v, -1.0);
-  double p = ctb_edd_H[CTB_EDD_H_N - 1];
+  // even/odd split H(t) = E(t^2) + t*O(t^2): two independent Horner chains of 8 instead of one of
+  // 16 (the Snyder kernels stall on this dependency chain: 4 warps per scheduler); same 3.5e-16.
+  static_assert(CTB_EDD_H_N == 17, "even/odd split below assumes degree 16");
+  const double t2 = t * t;
+  double pe = ctb_edd_H[16], po = ctb_edd_H[15];
 #pragma unroll
-  for (int k = CTB_EDD_H_N - 2; k >= 0; --k) p = fma(p, t, ctb_edd_H[k]);
-  return v * sqrt(v) * p;
+  for (int k = 14; k >= 0; k -= 2) pe = fma(pe, t2, ctb_edd_H[k]);
+#pragma unroll
+  for (int k = 13; k >= 1; k -= 2) po = fma(po, t2, ctb_edd_H[k]);
+  return v * sqrt(v) * fma(po, t, pe);
 }
 
 __device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double rW,
