@@ -280,6 +280,7 @@ TRANSFER_BYTES = {"h2d": 0, "d2h": 0}   # bytes actually copied across PCIe by t
 # block whenever the previous one is not provably idle -- so the blocks are pooled here and return to
 # the pool when the last numpy view of a result is garbage collected.
 _RESULT_POOL = {}
+_RESULT_OUT = {}    # size -> number of blocks ever allocated (in the pool or out with a result)
 
 
 class _PinnedOwner:
@@ -299,7 +300,16 @@ def pinned_result_like(t):
     import weakref
     nbytes = max(1, t.numel() * t.element_size())
     free = _RESULT_POOL.setdefault(nbytes, [])
-    block = free.pop() if free else torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    if not free and _RESULT_OUT.get(nbytes, 0) > 0:
+        # blocks of this size are out with results that may already be unreachable but sit in a
+        # reference cycle: a collection (tens of ms) is far cheaper than a fresh cudaHostAlloc
+        import gc
+        gc.collect()
+    if free:
+        block = free.pop()
+    else:
+        block = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        _RESULT_OUT[nbytes] = _RESULT_OUT.get(nbytes, 0) + 1
     view = block[: t.numel() * t.element_size()].view(t.dtype).view(t.shape)
     owner = _PinnedOwner(block, t.shape, np.dtype(str(t.dtype).replace("torch.", "")).str)
     arr = np.asarray(owner)
