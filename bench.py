@@ -381,6 +381,7 @@ def run_ours(args):
                "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
                "host_input_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
                "ms_per_step": dt * 1e3, "days_per_step": T, "step_ms": step_ms, "warmup_calls": n_w,
+               "pinned_result_blocks_allocated": int(sum(E._RESULT_OUT.values())),
                "steps": e2e_steps, "api": "weighted_aggregate_grid_to_regions(ds[numpy over pinned host "
                "memory], ...) -> Dataset[numpy]: host packing of the referenced gridcells + pinned chunked "
                "H2D + fused kernel + pinned D2H",
