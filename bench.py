@@ -202,7 +202,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:   # ranks share the host cores for the e2e packing
-        os.environ.setdefault("CTB_PACK_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+        os.environ.setdefault("CTB_PACK_THREADS", str(max(1, (3 * (os.cpu_count() or 1)) // (4 * world))))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

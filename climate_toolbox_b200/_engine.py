@@ -361,7 +361,15 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
                        N.VARIANT_STAGED | 0x100, out, 0, None, None)
 
     if not threads:
-        threads = int(os.environ.get("CTB_PACK_THREADS", "0"))   # 0 = all cores
+        threads = int(os.environ.get("CTB_PACK_THREADS", "0"))
+    if not threads:
+        # three quarters of the usable cores: with every core packing, the CUDA driver's own threads
+        # and the caller get descheduled and single calls take 2-3x longer (profiles/r1_e2e_notes.md)
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        threads = max(1, (3 * ncpu) // 4)
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     copy_stream.wait_stream(main)
