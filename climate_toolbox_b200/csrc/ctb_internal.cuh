@@ -59,8 +59,8 @@ struct CtbSeg {
 };
 static_assert(sizeof(CtbBlobHeader) == 32 && sizeof(CtbSeg) == 16, "blob layout");
 
-// fused kernel geometry: CTAs of up to 16 warps, two per SM; every thread stages 8 16-byte
-// loads per batch, so a 16-warp CTA fills a 128-unit tile in one batch.
+// fused kernel geometry: CTAs of up to 16 warps, two per SM; every thread stages 4 (16-warp CTAs)
+// or 8 (8-warp CTAs) 16-byte loads per batch, so a CTA fills a 128-unit tile in two batches.
 // Shared memory is deliberately limited to 164 KB per SM (82 KB per CTA): it is carved out
 // of the L1, and the L1 that is left bounds the loads in flight -- measured
 // (bench_micro/stage_bw3.py): 4.2 TB/s of staging traffic with <= 164 KB/SM, 2.9 TB/s with
