@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import hashlib
 import os
+import threading
 from collections import OrderedDict
 
 import numpy as np
@@ -19,7 +20,7 @@ import torch
 
 from . import _native as N
 
-__all__ = ["Plan", "GridSpec", "get_plan", "aggregate_device", "aggregate_host",
+__all__ = ["Plan", "GridSpec", "TimeGroups", "get_plan", "get_time_groups", "aggregate_device", "aggregate_host",
            "materialize_deferred", "default_device", "launch_count"]
 
 _NP2CTB = {np.dtype("float32"): N.F32, np.dtype("float64"): N.F64}
@@ -127,11 +128,47 @@ _PLAN_CACHE_SIZE = 8
 _PLAN_FAST = {}   # fingerprint of (DataFrame object, columns, grid) -> content key
 
 
-def _bitsum(a):
-    """Cheap order-insensitive fingerprint of a float column: sum of the raw 64-bit patterns
-    (mod 2^64) -- 10x faster than a nansum, and NaN payloads count too."""
-    a = np.ascontiguousarray(a, dtype=np.float64)
-    return int(a.view(np.uint64).sum(dtype=np.uint64))
+_FP_MULT = None
+
+
+def _buf_fp(u8):
+    """Position-sensitive 64-bit fingerprint of a byte buffer: sum_i word_i * odd_i (mod 2^64) over the
+    64-bit words with a fixed table of odd multipliers (0.3 ms for the 3.4 MB of a 420k-row column;
+    swapping two different words, or editing any word, changes it)."""
+    global _FP_MULT
+    n8 = u8.size // 8
+    h = int(u8.size)
+    if n8:
+        w = u8[: n8 * 8].view(np.uint64)
+        if _FP_MULT is None or _FP_MULT.size < min(n8, 1 << 16):
+            _FP_MULT = np.random.default_rng(0x5EED).integers(0, 1 << 63, 1 << 16, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+        with np.errstate(over="ignore"):
+            for c, i in enumerate(range(0, n8, 1 << 16)):
+                blk = w[i: i + (1 << 16)]
+                part = int((blk * _FP_MULT[: blk.size]).sum(dtype=np.uint64))
+                h = (h * 0x9E3779B97F4A7C15 + part + c) & 0xFFFFFFFFFFFFFFFF
+    if u8.size % 8:
+        h = (h * 31 + int.from_bytes(u8[n8 * 8:].tobytes(), "little")) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _col_fp(values):
+    """Content fingerprint of one weights column, position-sensitive, for the plan-cache fast path.
+    Numeric columns and Arrow-backed string columns (the pandas >= 3 default) are hashed from their
+    buffers; object columns through the (cached) hashes of their elements."""
+    pa = getattr(values, "_pa_array", None)
+    if pa is not None:
+        h = [len(values)]
+        for ch in pa.chunks:
+            h.append((ch.offset, len(ch), ch.null_count))
+            for b in ch.buffers():
+                h.append(-1 if b is None else _buf_fp(np.frombuffer(b, dtype=np.uint8)))
+        return tuple(h)
+    a = np.asarray(values)
+    if a.dtype == object or a.dtype.kind in "US":
+        return hash(tuple(a.tolist()))
+    a = np.ascontiguousarray(a)
+    return (str(a.dtype), _buf_fp(a.view(np.uint8).reshape(-1)))
 
 
 def region_codes(labels):
@@ -149,8 +186,9 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
         if col not in weights:
             raise KeyError(col)
     # fast path: the same DataFrame object asked for again (the reference memoises its weights
-    # frame per path, aggregations.py:127).  Guarded by cheap fingerprints of the columns used,
-    # so an in-place edit of the frame still rebuilds the plan.
+    # frame per path, aggregations.py:127).  Guarded by position-sensitive content fingerprints of
+    # EVERY column the plan is built from -- the region column included -- so an in-place edit or
+    # permutation of the frame rebuilds the plan (about 2 ms per call at 420k rows).
     fp = None
     if cache:
         gh = hashlib.sha1()
@@ -159,9 +197,8 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
             fp = (id(weights), len(weights), aggwt, agglev, backup_aggwt, stage_bytes, smem_budget,
                   bool(compact), int(elem_bytes), str(device), gh.hexdigest(),
                   # `trusted`: a private frame of the caller (never edited in place): identity is enough
-                  () if trusted else tuple(_bitsum(weights[c].values) for c in ("lat", "lon", aggwt, backup_aggwt)),
-                  str(weights[agglev].values[0]) if len(weights) else "",
-                  str(weights[agglev].values[-1]) if len(weights) else "")
+                  () if trusted else tuple(_col_fp(weights[c].values)
+                                           for c in ("lat", "lon", aggwt, backup_aggwt, agglev)))
         hit = _PLAN_FAST.get(fp)
         if hit is not None and hit in _PLAN_CACHE:
             _PLAN_CACHE.move_to_end(hit)
@@ -209,6 +246,48 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     return plan
 
 
+class TimeGroups:
+    """Owns a ``ctb_time_groups*``: the output column of every day for the fused time reduction
+    (annual sums).  ``group_of_day``: int array, starts at 0, grows by 0 or 1 per day."""
+
+    def __init__(self, group_of_day, device):
+        g = np.ascontiguousarray(group_of_day, dtype=np.int32)
+        self._h = C.c_void_p()
+        self.device = device
+        self.T = int(g.size)
+        N.check(N.lib().ctb_time_groups_create(_ip(g) if g.size else None, g.size, device.index or 0,
+                                               C.byref(self._h)))
+        self.n_groups = int(N.lib().ctb_time_groups_count(self._h))
+
+    def close(self):
+        if self._h:
+            N.lib().ctb_time_groups_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_GROUPS_CACHE: "OrderedDict[tuple, TimeGroups]" = OrderedDict()
+
+
+def get_time_groups(group_of_day, device=None):
+    device = device or default_device()
+    g = np.ascontiguousarray(group_of_day, dtype=np.int32)
+    key = (str(device), g.size, hashlib.sha1(g.tobytes()).hexdigest())
+    hit = _GROUPS_CACHE.get(key)
+    if hit is None:
+        hit = _GROUPS_CACHE[key] = TimeGroups(g, device)
+        while len(_GROUPS_CACHE) > 16:
+            _GROUPS_CACHE.popitem(last=False)
+    else:
+        _GROUPS_CACHE.move_to_end(key)
+    return hit
+
+
 def _params_array(kind, params):
     a = np.ascontiguousarray(params, dtype=np.float64)
     return a, (_dp(a) if a.size else None)
@@ -219,36 +298,53 @@ def _stream_ptr(device, stream=None):
     return C.c_void_p(s.cuda_stream)
 
 
+def _workspace(plan, T, n_out, layout, variant, groups, workspace):
+    L = N.lib()
+    staged = (variant & 0xff) != N.VARIANT_DIRECT and layout == N.LAYOUT_TIME_MAJOR
+    if groups is not None:
+        ws_bytes = L.ctb_aggregate_grouped_workspace_bytes(plan._h, groups._h, n_out)
+    else:
+        ws_bytes = L.ctb_aggregate_workspace_bytes(plan._h, T, n_out) if staged else 0
+    if ws_bytes and (workspace is None or workspace.numel() * 8 < ws_bytes):
+        workspace = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=plan.device)
+    return workspace
+
+
 def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out, variant, out, out_ld,
-            workspace, stream):
-    """Raw-pointer call of ctb_aggregate (p0/p1: device or mapped-host addresses)."""
+            workspace, stream, groups=None, t_begin=0, flush=True):
+    """Raw-pointer call of ctb_aggregate / ctb_aggregate_grouped (p0/p1: device or mapped-host
+    addresses).  With ``groups`` the result is [n_out, R, n_groups]."""
     dev = plan.device
     L = N.lib()
     if out is None:
-        out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
-    ws_bytes = L.ctb_aggregate_workspace_bytes(plan._h, T, n_out) \
-        if (variant & 0xff) != N.VARIANT_DIRECT and layout == N.LAYOUT_TIME_MAJOR else 0
-    if ws_bytes and (workspace is None or workspace.numel() * 8 < ws_bytes):
-        workspace = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
+        out = torch.empty((n_out, plan.R, T if groups is None else groups.n_groups), dtype=torch.float64,
+                          device=dev)
+    workspace = _workspace(plan, T, n_out, layout, variant, groups, workspace)
     tix_d = plan.time_index_device(tix)
     pa, pp = _params_array(kind, params)
-    rc = L.ctb_aggregate(
-        plan._h, C.c_void_p(p0), C.c_void_p(p1) if p1 else None, ctb_dtype, layout, int(stride),
-        C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
-        _KIND[kind], pp, int(pa.size), int(n_out), C.c_void_p(out.data_ptr()), int(out_ld),
-        C.c_void_p(workspace.data_ptr()) if workspace is not None else None,
-        int(workspace.numel() * 8) if workspace is not None else 0, int(variant),
-        _stream_ptr(dev, stream))
+    head = (plan._h, C.c_void_p(p0), C.c_void_p(p1) if p1 else None, ctb_dtype, layout, int(stride),
+            C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
+            _KIND[kind], pp, int(pa.size), int(n_out))
+    tail = (C.c_void_p(out.data_ptr()), int(out_ld),
+            C.c_void_p(workspace.data_ptr()) if workspace is not None else None,
+            int(workspace.numel() * 8) if workspace is not None else 0, int(variant),
+            _stream_ptr(dev, stream))
+    if groups is None:
+        rc = L.ctb_aggregate(*head, *tail)
+    else:
+        rc = L.ctb_aggregate_grouped(*head, groups._h, int(t_begin), 1 if flush else 0, *tail)
     N.check(rc)
     return out
 
 
 def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", params=(), n_out=1,
-                     variant=N.VARIANT_AUTO, out=None, out_ld=0, stream=None, workspace=None):
+                     variant=N.VARIANT_AUTO, out=None, out_ld=0, stream=None, workspace=None, groups=None,
+                     t_begin=0, flush=True):
     """Launch the fused kernel on device-resident inputs.
 
     ``x0`` / ``x1``: contiguous CUDA tensors (f32/f64).  ``tix``: numpy int array of
-    physical time positions or None.  Returns ``out`` ([n_out, R, T] float64 CUDA).
+    physical time positions or None.  Returns ``out`` ([n_out, R, T] float64 CUDA; with
+    ``groups`` -- a :class:`TimeGroups` -- [n_out, R, n_groups]: the days of every group summed).
     """
     dev = plan.device
     if x0.device != dev or not x0.is_contiguous():
@@ -258,7 +354,8 @@ def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", para
     if x1 is not None and (x1.dtype != x0.dtype or x1.shape != x0.shape):
         raise ValueError("the two inputs must agree in dtype and shape")
     return _launch(plan, x0.data_ptr(), x1.data_ptr() if x1 is not None else 0, _T2CTB[x0.dtype], layout,
-                   stride, tix, T, kind, params, n_out, variant, out, out_ld, workspace, stream)
+                   stride, tix, T, kind, params, n_out, variant, out, out_ld, workspace, stream, groups,
+                   t_begin, flush)
 
 
 def _all_pinned(xs):
@@ -268,7 +365,11 @@ def _all_pinned(xs):
         return False
 
 
-_PINNED = {}   # (slot, k) -> pinned staging tensor for packed chunks (reused across calls)
+# (device index, slot, k) -> [pinned staging tensor for packed chunks, event of the last H2D copy that
+# read it].  The buffers are reused across calls, so the event outlives the call that recorded it: a
+# later call (or another thread) waits for it before it packs into the buffer again.
+_PINNED = {}
+_HOST_LOCK = threading.Lock()   # one packed host call at a time: they share the buffers and the cores
 TRANSFER_BYTES = {"h2d": 0, "d2h": 0}   # bytes actually copied across PCIe by this module (bench e2e)
 
 
@@ -318,16 +419,34 @@ def pinned_result_like(t):
 
 
 def _pinned_buffer(key, nbytes):
-    b = _PINNED.get(key)
-    if b is None or b.numel() < nbytes:
-        b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        _PINNED[key] = b
-    return b
+    """Staging buffer `key`, idle: waits for the last H2D copy that read it (this or an earlier call)."""
+    ent = _PINNED.get(key)
+    if ent is not None and ent[1] is not None:
+        ent[1].synchronize()
+        ent[1] = None
+    if ent is None or ent[0].numel() < nbytes:
+        ent = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True), None]
+        _PINNED[key] = ent
+    return ent
+
+
+def pack_threads():
+    """Host threads ``ctb_host_pack`` may use: CTB_PACK_THREADS, else three quarters of the usable
+    cores (with every core packing, the CUDA driver's own threads and the caller get descheduled and
+    single calls take 2-3x longer, profiles/r1_e2e_notes.md)."""
+    threads = int(os.environ.get("CTB_PACK_THREADS", "0"))
+    if threads:
+        return threads
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    return max(1, (3 * ncpu) // 4)
 
 
 def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(), n_out=1,
-                   variant=N.VARIANT_AUTO, chunk_bytes=192 << 20, zero_copy=None, threads=0):
-    """Host (numpy) inputs -> CUDA tensor [n_out, R, T].
+                   variant=N.VARIANT_AUTO, chunk_bytes=192 << 20, zero_copy=None, threads=0, groups=None):
+    """Host (numpy) inputs -> CUDA tensor [n_out, R, T] (with ``groups``: [n_out, R, n_groups]).
 
     ``xs``: list of 1 or 2 C-contiguous numpy arrays viewed as 2-D
     (TIME_MAJOR: [t_phys, stride]; CELL_MAJOR: [ncell, stride]).
@@ -340,14 +459,15 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
       place by the kernel (zero-copy).
     """
     dev = plan.device
-    out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
+    n_cols = T if groups is None else groups.n_groups
+    out = torch.empty((n_out, plan.R, n_cols), dtype=torch.float64, device=dev)
     if T == 0 or plan.R == 0:
-        return out
+        return out.zero_() if groups is not None else out
     if layout == N.LAYOUT_CELL_MAJOR:
         d = [torch.from_numpy(x).to(dev, non_blocking=True) for x in xs]
         TRANSFER_BYTES["h2d"] += sum(x.nbytes for x in xs)
         return aggregate_device(plan, d[0], d[1] if len(d) > 1 else None, layout, stride, tix, T,
-                                kind, params, n_out, variant, out=out)
+                                kind, params, n_out, variant, out=out, groups=groups)
     if zero_copy is None:
         # opt-in: on the round-1 box the in-place read moved 2.5 GB at ~7 GB/s (16-byte requests
         # over PCIe) and lost to copying all 6 GB at ~21 GB/s (profiles/r1_e2e_notes.md)
@@ -358,18 +478,9 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
         # referenced gridcells (~30 % of a global land/ocean grid) cross the bus
         return _launch(plan, xs[0].ctypes.data, xs[1].ctypes.data if len(xs) > 1 else 0,
                        _NP2CTB[xs[0].dtype], layout, stride, tix, T, kind, params, n_out,
-                       N.VARIANT_STAGED | 0x100, out, 0, None, None)
+                       N.VARIANT_STAGED | 0x100, out, 0, None, None, groups)
 
-    if not threads:
-        threads = int(os.environ.get("CTB_PACK_THREADS", "0"))
-    if not threads:
-        # three quarters of the usable cores: with every core packing, the CUDA driver's own threads
-        # and the caller get descheduled and single calls take 2-3x longer (profiles/r1_e2e_notes.md)
-        try:
-            ncpu = len(os.sched_getaffinity(0))
-        except AttributeError:
-            ncpu = os.cpu_count() or 1
-        threads = max(1, (3 * ncpu) // 4)
+    threads = threads or pack_threads()
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     copy_stream.wait_stream(main)
@@ -377,59 +488,67 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
     itemsize = xs[0].dtype.itemsize
     width = plan.info["n_packed_cells"] if plan.compact else xs[0].shape[1]
     days = max(32, int(chunk_bytes // max(width * itemsize * len(xs), 1)) // 32 * 32)
-    ws = None
-    ws_bytes = N.lib().ctb_aggregate_workspace_bytes(plan._h, min(days, T), n_out)
-    if ws_bytes:
-        ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
+    # one workspace for the whole call: split-region rows of a chunk, or -- with time groups -- of
+    # the whole time axis plus the per-tile partial sums
+    ws = _workspace(plan, min(days, T), n_out, layout, variant, groups, None)
     tdt = torch.float32 if itemsize == 4 else torch.float64
-    dbuf, free_ev, h2d_ev = {}, {}, {}
+    dbuf, free_ev = {}, {}
     ts = None if plan.compact else [torch.from_numpy(x) for x in xs]
-    for ci, t0 in enumerate(range(0, T, days)):
-        t1 = min(T, t0 + days)
-        n = t1 - t0
-        slot = ci % 2
-        rel = None
-        if plan.compact:
-            # pack on the host (all cores, GIL released) while the previous chunk is in flight
-            if slot in h2d_ev:
-                h2d_ev[slot].synchronize()          # the pinned buffer is free again
-            pins = []
-            for k, x in enumerate(xs):
-                pb = _pinned_buffer((slot, k), days * width * itemsize)
-                N.check(N.lib().ctb_host_pack(
-                    plan._h, C.c_void_p(x.ctypes.data), _NP2CTB[x.dtype], int(stride),
-                    tix_full.ctypes.data_as(C.POINTER(C.c_int64)) if tix_full is not None else None,
-                    int(t0), int(n), C.c_void_p(pb.data_ptr()), int(threads)))
-                pins.append(pb[: n * width * itemsize].view(tdt).view(n, width))
-            srcs = pins
-        else:
-            sub = np.arange(t0, t1) if tix_full is None else tix_full[t0:t1]
-            lo, hi = int(sub.min()), int(sub.max()) + 1
-            srcs = [t[lo:hi] for t in ts]
-            if tix_full is not None and not np.array_equal(sub - lo, np.arange(n)):
-                rel = sub - lo
-        with torch.cuda.stream(copy_stream):
-            if slot in free_ev:
-                copy_stream.wait_event(free_ev[slot])
-            cur = []
-            for k, src in enumerate(srcs):
-                b = dbuf.get((slot, k))
-                if b is None or b.shape[0] < src.shape[0]:
-                    b = torch.empty((max(src.shape[0], days + 8), src.shape[1]), dtype=tdt, device=dev)
-                    b.record_stream(main)
-                    dbuf[(slot, k)] = b
-                b[: src.shape[0]].copy_(src, non_blocking=True)
-                TRANSFER_BYTES["h2d"] += src.numel() * src.element_size()
-                cur.append(b)
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
-            h2d_ev[slot] = ready
-        main.wait_event(ready)
-        aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, width, rel, n, kind,
-                         params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        free_ev[slot] = ev
+    di = dev.index or 0
+    starts = list(range(0, T, days))
+    with _HOST_LOCK:
+        for ci, t0 in enumerate(starts):
+            t1 = min(T, t0 + days)
+            n = t1 - t0
+            slot = ci % 2
+            rel = None
+            pin_ents = []
+            if plan.compact:
+                # pack on the host (GIL released) while the previous chunk is in flight
+                pins = []
+                for k, x in enumerate(xs):
+                    ent = _pinned_buffer((di, slot, k), days * width * itemsize)   # waits for its last H2D
+                    pin_ents.append(ent)
+                    N.check(N.lib().ctb_host_pack(
+                        plan._h, C.c_void_p(x.ctypes.data), _NP2CTB[x.dtype], int(stride),
+                        tix_full.ctypes.data_as(C.POINTER(C.c_int64)) if tix_full is not None else None,
+                        int(t0), int(n), C.c_void_p(ent[0].data_ptr()), int(threads)))
+                    pins.append(ent[0][: n * width * itemsize].view(tdt).view(n, width))
+                srcs = pins
+            else:
+                sub = np.arange(t0, t1) if tix_full is None else tix_full[t0:t1]
+                lo, hi = int(sub.min()), int(sub.max()) + 1
+                srcs = [t[lo:hi] for t in ts]
+                if tix_full is not None and not np.array_equal(sub - lo, np.arange(n)):
+                    rel = sub - lo
+            with torch.cuda.stream(copy_stream):
+                if slot in free_ev:
+                    copy_stream.wait_event(free_ev[slot])
+                cur = []
+                for k, src in enumerate(srcs):
+                    b = dbuf.get((slot, k))
+                    if b is None or b.shape[0] < src.shape[0]:
+                        b = torch.empty((max(src.shape[0], days + 8), src.shape[1]), dtype=tdt, device=dev)
+                        b.record_stream(main)
+                        dbuf[(slot, k)] = b
+                    b[: src.shape[0]].copy_(src, non_blocking=True)
+                    TRANSFER_BYTES["h2d"] += src.numel() * src.element_size()
+                    cur.append(b)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+                for ent in pin_ents:
+                    ent[1] = ready      # outlives this call: the next packer of the buffer waits for it
+            main.wait_event(ready)
+            if groups is None:
+                aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, width, rel, n, kind,
+                                 params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
+            else:
+                aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, width, rel, n, kind,
+                                 params, n_out, variant, out=out, workspace=ws, groups=groups, t_begin=t0,
+                                 flush=(t0 == starts[-1]))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            free_ev[slot] = ev
     return out
 
 

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctb.so")
+# CTB_LIBRARY: path of a development build of the library (bench_micro/ experiments)
+LIB_PATH = os.environ.get("CTB_LIBRARY") or os.path.join(_HERE, "libctb.so")
 
 OK, ERR_LABEL_NOT_FOUND, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED = range(5)
 F32, F64 = 0, 1
@@ -23,7 +24,8 @@ SYMBOLS = (
     "ctb_version", "ctb_last_error", "ctb_launch_count", "ctb_plan_build", "ctb_plan_free",
     "ctb_plan_get_info", "ctb_plan_row_cells", "ctb_plan_den", "ctb_plan_row_weights",
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
-    "ctb_debug_stage_bw", "ctb_debug_cpasync_bw", "ctb_host_pack",
+    "ctb_host_pack", "ctb_time_groups_create", "ctb_time_groups_free", "ctb_time_groups_count",
+    "ctb_aggregate_grouped_workspace_bytes", "ctb_aggregate_grouped",
 )
 
 
@@ -40,6 +42,7 @@ class PlanInfo(C.Structure):
         ("n_split_regions", C.c_int32), ("n_scratch_slots", C.c_int32),
         ("cap_cells", C.c_int32), ("max_bundle_cells", C.c_int32), ("time_block", C.c_int32),
         ("max_region_rows", C.c_int32), ("max_meta_bytes", C.c_int32), ("n_packed_cells", C.c_int32),
+        ("n_quads", C.c_int64), ("n_quads_conflict", C.c_int64),
     ]
 
     def as_dict(self):
@@ -85,10 +88,17 @@ def lib():
     L.ctb_transform.argtypes = [vp, vp, C.c_int, i64, C.c_int, dp, C.c_int, C.c_int, vp, vp]
     L.ctb_gather_rows.restype = C.c_int
     L.ctb_gather_rows.argtypes = [p, vp, C.c_int, C.c_int, i64, vp, i64, vp, vp]
-    L.ctb_debug_stage_bw.restype = C.c_int
-    L.ctb_debug_stage_bw.argtypes = [p, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
-    L.ctb_debug_cpasync_bw.restype = C.c_int
-    L.ctb_debug_cpasync_bw.argtypes = [p, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp]
+    L.ctb_time_groups_create.restype = C.c_int
+    L.ctb_time_groups_create.argtypes = [ip, i64, C.c_int, C.POINTER(p)]
+    L.ctb_time_groups_free.restype = None
+    L.ctb_time_groups_free.argtypes = [p]
+    L.ctb_time_groups_count.restype = i32
+    L.ctb_time_groups_count.argtypes = [p]
+    L.ctb_aggregate_grouped_workspace_bytes.restype = C.c_size_t
+    L.ctb_aggregate_grouped_workspace_bytes.argtypes = [p, p, C.c_int]
+    L.ctb_aggregate_grouped.restype = C.c_int
+    L.ctb_aggregate_grouped.argtypes = [p, vp, vp, C.c_int, C.c_int, i64, vp, i64, C.c_int, dp, C.c_int,
+                                        C.c_int, p, i64, C.c_int, vp, i64, vp, C.c_size_t, C.c_int, vp]
     L.ctb_host_pack.restype = C.c_int
     L.ctb_host_pack.argtypes = [p, vp, C.c_int, i64, C.POINTER(C.c_int64), i64, i64, vp, C.c_int]
     _lib = L

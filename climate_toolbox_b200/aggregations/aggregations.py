@@ -118,16 +118,53 @@ def _coord_labels(ds, name):
     return np.asarray(ds._coords[name].values, dtype=np.float64)
 
 
-def _run_group(plan, views, kind, params, n_out, variant):
+def _run_group(plan, views, kind, params, n_out, variant, groups=None):
     """One fused launch for `n_out` outputs sharing the same sources."""
     v0 = views[0]
     if v0.on_device:
         out = E.aggregate_device(plan, views[0].data2d, views[1].data2d if len(views) > 1 else None,
-                                 v0.layout, v0.stride, v0.tix, v0.T, kind, params, n_out, variant)
+                                 v0.layout, v0.stride, v0.tix, v0.T, kind, params, n_out, variant,
+                                 groups=groups)
     else:
         out = E.aggregate_host(plan, [v.data2d for v in views], v0.layout, v0.stride, v0.tix, v0.T,
-                               kind, params, n_out, variant)
+                               kind, params, n_out, variant, groups=groups)
     return out
+
+
+def _time_group_ids(ds, dim, n, spec):
+    """``time_groups=`` of :func:`weighted_aggregate_grid_to_regions` -> (group id of every step,
+    group labels).  ``"year"``: the calendar year of a datetime coordinate, or ``YYYYDDD // 1000`` of
+    the integer time ``tas_poly`` writes; an int ``p``: blocks of ``p`` consecutive steps; an array:
+    one label per step.  Groups must be runs of consecutive steps."""
+    if isinstance(spec, str):
+        if spec != "year":
+            raise ValueError("time_groups={!r}: expected 'year', a block length or one label per step".format(spec))
+        if dim not in ds._coords:
+            raise KeyError(dim)
+        c = np.asarray(ds._coords[dim].values)
+        if np.issubdtype(c.dtype, np.datetime64):
+            lab = c.astype("datetime64[Y]").astype(np.int64) + 1970
+        elif np.issubdtype(c.dtype, np.integer):
+            lab = c.astype(np.int64) // 1000
+        else:
+            lab = pd.DatetimeIndex(c).year.values.astype(np.int64)
+    elif np.isscalar(spec):
+        p = int(spec)
+        if p <= 0:
+            raise ValueError("time_groups block length must be positive")
+        lab = np.arange(n, dtype=np.int64) // p
+    else:
+        lab = np.asarray(spec)
+    if len(lab) != n:
+        raise ValueError("time_groups gives {} labels for {} steps".format(len(lab), n))
+    change = np.ones(n, dtype=bool)
+    if n:
+        change[1:] = lab[1:] != lab[:-1]
+    gid = np.cumsum(change) - 1
+    labels = lab[change]
+    if len(set(labels.tolist())) != len(labels):
+        raise ValueError("time_groups: every group must be one run of consecutive steps")
+    return gid.astype(np.int32), labels
 
 
 def _group_requests(reqs):
@@ -155,7 +192,8 @@ def _group_requests(reqs):
 
 
 def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant=N.VARIANT_AUTO,
-                    device=None, smem_budget=0, keep_on_device=False, pack_host=True, trusted_weights=False):
+                    device=None, smem_budget=0, keep_on_device=False, pack_host=True, trusted_weights=False,
+                    time_groups=None, time_dim="time"):
     lat, lon = _coord_labels(ds, "lat"), _coord_labels(ds, "lon")
     reqs = []
     for name in variables:
@@ -181,7 +219,17 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
                           smem_budget=smem_budget, compact=compact, elem_bytes=v0.elem_bytes,
                           trusted=trusted_weights)
         n_out = len(g["names"])
-        out = _run_group(plan, views, g["kind"], g["params"], n_out, variant)  # [n_out, R, T]
+        groups = glabels = None
+        other_shape = v0.other_shape
+        if time_groups is not None:
+            # fused time reduction: the days of every group are summed inside the kernel
+            if v0.other_dims != (time_dim,):
+                raise NotImplementedError("time_groups needs variables over ({}, lat, lon), got {}".format(
+                    time_dim, v0.out_dims_template))
+            gid, glabels = _time_group_ids(ds, time_dim, v0.T, time_groups)
+            groups = E.get_time_groups(gid, dev)
+            other_shape = (groups.n_groups,)
+        out = _run_group(plan, views, g["kind"], g["params"], n_out, variant, groups)  # [n_out, R, T]
         # reference dim order: agglev takes the place of the first of (lat, lon)
         tmpl = ds._vars[g["names"][0]].dims
         first = min(tmpl.index("lat"), tmpl.index("lon"))
@@ -198,7 +246,7 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
             torch.cuda.current_stream(out.device).synchronize()
         R = plan.R
         for j, name in enumerate(g["names"]):
-            a = res[j].reshape((R,) + v0.other_shape)      # (agglev, *others) in view order
+            a = res[j].reshape((R,) + other_shape)         # (agglev, *others) in view order
             cur = [agglev] + list(v0.other_dims)
             want = list(others)
             want.insert(first, agglev)
@@ -207,7 +255,9 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
             out_ds[name] = Variable(tuple(want), a, ds._vars[name].attrs)
         out_ds._coords[agglev] = Variable((agglev,), np.asarray(plan.region_labels))
         for d in others:
-            if d in ds._coords:
+            if glabels is not None and d == time_dim:
+                out_ds._coords[d] = Variable((d,), np.asarray(glabels))
+            elif d in ds._coords:
                 out_ds._coords[d] = Variable((d,), ds._coords[d].values, ds._coords[d].attrs)
     return out_ds
 
@@ -368,6 +418,11 @@ def weighted_aggregate_grid_to_regions(ds, variable, aggwt, agglev, weights=None
         :func:`prepare_spatial_weights_data`) with columns lat, lon, agglev, aggwt
         and ``backup_aggwt``.  ``None`` raises ``TypeError`` exactly like the
         reference (``:118-119`` calls a one-argument function without arguments).
+    time_groups : extension (``engine_opts``), default None.  ``"year"``, a block length or one
+        label per time step: the daily region values of every group are SUMMED inside the kernel
+        (``EDD_P = sum_d EDD_d``, reference ``transformations.py:17-21``) and the result has one
+        time step per group -- equal to ``out.groupby(label).sum()`` of the daily result, without
+        ever writing the region x day block.
 
     Returns
     -------
@@ -425,7 +480,7 @@ def weighted_aggregate_grid_to_regions_multi(ds, variable, aggwts, agglev, weigh
         raise TypeError("weighted_aggregate_grid_to_regions_multi takes one variable name")
     key = (id(weights), tuple(aggwts), agglev, backup_aggwt, len(weights))
     hit = _STACKED.get(key)
-    sums = tuple(E._bitsum(weights[c].values) for c in aggwts + [backup_aggwt, "lat", "lon"])
+    sums = tuple(E._col_fp(weights[c].values) for c in aggwts + [backup_aggwt, "lat", "lon", agglev])
     if hit is not None and hit[0] is weights and hit[2] == sums:
         stacked, labels, present = hit[1], hit[3], hit[4]
     else:

@@ -34,46 +34,60 @@ extern std::atomic<int64_t> g_ctb_launches;
   } while (0)
 
 // ------------------------------------------------------------- constants ---
-constexpr int CTB_TB = 32;             // days per staging tile (one warp of lanes)
-constexpr int CTB_S = CTB_TB + 1;      // smem row stride in elements: odd => conflict-free
+constexpr int CTB_TB = 32;             // days per staging tile
+constexpr int CTB_S = CTB_TB + 1;      // transposed tile (Snyder kernel): row stride in elements, odd => conflict-free
 constexpr int CTB_PIECE = 4;           // gridcells per staged piece (16 B of f32)
-constexpr int CTB_STAGE_THREADS = 256; // 8 warps: each stages 4 days x 8 pieces per step
 
-// Per-bundle metadata blob, copied to shared memory with one cp.async.bulk:
+// Per-bundle metadata blob (one cp.async.bulk into shared memory per work unit):
 //   part A: [CtbBlobHeader][n_pieces x int32 piece]
-//   part B: [n_seg x CtbSeg][n_ent_pad x double w][n_ent_pad x uint32 off]
-//           off = byte offset of the entry's staged cell row in the tile: cell * 33 * elem_bytes
-// (every section 16-byte aligned; every segment's entries start at a multiple of 4;
-//  off_* are byte offsets from the start of part B)
+//   part B: [n_seg x CtbSeg][n_ent_pad x CtbEnt]
+// Every segment's entries start at a multiple of 4 ("quads"); a quad holds, whenever the
+// region's cells allow it, four staged columns with four different residues mod 4, in residue
+// order -- the streaming kernel reads a quad with one conflict-free shared-memory load
+// (lane = entry-in-quad x 8 days).  Ranges are padded to whole quads with weight-0 entries.
 struct CtbBlobHeader {
   int32_t n_pieces, n_seg;
-  int32_t off_seg, off_w, off_loc;  // byte offsets from the start of part B
-  int32_t n_ent_pad, bytes_a, bytes_b;   // off_loc = offset of the uint32 `off` array
+  int32_t off_seg, off_ent;   // byte offsets from the start of part B
+  int32_t n_ent_pad, bytes_a, bytes_b, reserved;
 };
 struct CtbSeg {
   int32_t target;  // >= 0: region row of `out`; < 0: ~scratch_slot (region split over bundles)
   uint16_t e0_4;   // first entry / 4
-  uint16_t n;      // entries
+  uint16_t n;      // entries (without the padding)
   double rden;     // 1 / (sum of the region's weights); 1.0 for partial rows.  den == 0 gives
                    // inf: 0 * inf = NaN and x * inf = +-inf, like 0/0 and x/0
 };
-static_assert(sizeof(CtbBlobHeader) == 32 && sizeof(CtbSeg) == 16, "blob layout");
+struct CtbEnt {
+  double w;        // effective weight of the weights row (aggregations.py:73)
+  uint32_t off;    // byte offset of the staged gridcell's column in a tile row: column * elem_bytes
+  uint32_t pad;
+};
+static_assert(sizeof(CtbBlobHeader) == 32 && sizeof(CtbSeg) == 16 && sizeof(CtbEnt) == 16, "blob layout");
 
-// fused kernel geometry: CTAs of up to 16 warps, two per SM; every thread stages 4 (16-warp CTAs)
-// or 8 (8-warp CTAs) 16-byte loads per batch, so a CTA fills a 128-unit tile in two batches.
-// Shared memory is deliberately limited to 164 KB per SM (82 KB per CTA): it is carved out
-// of the L1, and the L1 that is left bounds the loads in flight -- measured
-// (bench_micro/stage_bw3.py): 4.2 TB/s of staging traffic with <= 164 KB/SM, 2.9 TB/s with
-// 196 KB, 2.1 TB/s with 228 KB.
-constexpr int CTB_TILE_UNITS = 128;                               // 16-byte units per day in a tile
+// A bundle stages at most CTB_TILE_UNITS 16-byte units per day and input.
+#ifdef CTB_TILE_UNITS_OVERRIDE
+constexpr int CTB_TILE_UNITS = CTB_TILE_UNITS_OVERRIDE;
+#else
+constexpr int CTB_TILE_UNITS = 128;
+#endif
+constexpr int CTB_META_A_CAP = 32 + CTB_TILE_UNITS * 4;           // header + piece list
+constexpr int CTB_META_B_CAP = 14304;                             // segment table + entries
+constexpr int CTB_META_CAP = CTB_META_A_CAP + CTB_META_B_CAP;     // 14,848 B: one whole blob
+
+// ---- streaming kernel (ctb_stream.cu): row-major tiles [day][column], filled by cp.async ----
+// Row pitch: 128 units + 16 bytes, == 16 (mod 128): the 8 days x 4 columns one warp reads per
+// shared-memory load fall into 32 different banks.
+constexpr int CTB_ROWB = CTB_TILE_UNITS * 16 + 16;                 // 2,064 B
+constexpr int CTB_STREAM_TILE_BYTES = CTB_TB * CTB_ROWB;           // 66,048 B per input
+constexpr int CTB_STREAM_THREADS = 1024;
+constexpr int CTB_STREAM_PRODUCER_WARPS = 4;
+
+// ---- Snyder kernel (ctb_agg.cu): transposed tiles [cell][day], CTAs of 8 warps, two per SM.
+// Shared memory is deliberately limited to 164 KB per SM: it is carved out of the L1, and the
+// L1 that is left bounds the register-staged loads in flight (bench_micro/stage_bw3.py).
 constexpr int CTB_TILE_BYTES = CTB_TILE_UNITS * 4 * CTB_S * 4;    // 67,584 B of shared memory
 constexpr int CTB_CTAS_PER_SM = 2;
-constexpr int CTB_SMEM_PER_CTA = 164 * 1024 / CTB_CTAS_PER_SM - 1024 - 512;  // 82,432 B
-// metadata blob: part A (header + piece list) and part B (segment table + weights +
-// staged-cell indices) are contiguous in global memory and arrive as ONE bulk copy
 constexpr int CTB_N_WORK_COUNTERS = 64;
-constexpr int CTB_META_A_CAP = 32 + CTB_TILE_UNITS * 4;
-constexpr int CTB_META_B_CAP = (CTB_SMEM_PER_CTA - CTB_TILE_BYTES - CTB_META_A_CAP) & ~15;
 
 // -------------------------------------------------------------- the plan ---
 struct ctb_plan {
@@ -92,7 +106,8 @@ struct ctb_plan {
   // staging bundles (device)
   int32_t n_bundles = 0, n_segments = 0;
   int64_t* d_b_blob_off = nullptr;   // [n_bundles+1] byte offsets into d_blob (16 B aligned)
-  int4* d_b_desc = nullptr;          // [n_bundles] {off_lo, off_hi, bytes_a, bytes_b}
+  int4* d_b_desc = nullptr;          // [n_bundles] {off_lo, off_hi, bytes_a + bytes_b, n_units}
+  int32_t* d_unit_tab = nullptr;     // [n_bundles][CTB_TILE_UNITS] element offset of every staged 16-byte unit in a day plane
   // dynamic unit scheduler of the fused kernel: CTB_N_WORK_COUNTERS device counters used round-robin,
   // one per launch (zeroed on the launch's stream), so that launches of one plan on different
   // streams do not share a counter
@@ -109,12 +124,25 @@ struct ctb_plan {
   std::vector<PackRun> h_pack_runs;
   int compact = 0;
   int elem_bytes = 4;   // element size the staged-cell byte offsets were built for
+  int stage_bytes = 4;  // staged bytes per gridcell-day the bundles were sized for (n_in * elem_bytes)
 
   // host mirrors for queries
   std::vector<int32_t> h_row_cell;
   std::vector<double> h_row_w;
   std::vector<double> h_den;
   ctb_plan_info info{};
+};
+
+// ---------------------------------------------------------- time groups ---
+// Fused time reduction (annual sums): output column of every day, contiguous groups.
+struct ctb_time_groups {
+  int device = 0;
+  int64_t T = 0;
+  int32_t n_groups = 0;
+  int32_t gk = 1;                    // max groups one 32-day tile touches
+  int32_t* d_group = nullptr;        // [T]
+  int32_t* d_t_lo = nullptr;         // [n_groups] first day of the group
+  int32_t* d_t_hi = nullptr;         // [n_groups] one past its last day
 };
 
 // ------------------------------------------------- gridcell transforms -----
@@ -216,6 +244,98 @@ __device__ __forceinline__ void ctb_apply(const CtbTr& P, double x0, double x1, 
       f[j] = ctb_edd(x0, x1, M, W, rW, P.a[2 * j]) - ctb_edd(x0, x1, M, W, rW, P.a[2 * j + 1]);
   }
 }
+
+// ------------------------------------------------ kernel arguments ---------
+struct AggArgs {
+  const void* x0;
+  const void* x1;
+  int64_t stride;
+  const int32_t* tix;
+  int T;
+  int64_t out_ld;
+  int64_t ncell;
+  int R;
+  double* out;
+  double* scratch;
+  int n_scratch;
+  const double* den;
+  const unsigned char* blob;
+  int n_bundles;
+  int n_items;
+  const int4* b_desc;
+  const int32_t* unit_tab;
+  int tile_stride;   // bytes between tile stages
+  int n_stages;      // streaming kernel: tile stages in shared memory
+  int n_tb;          // time blocks: ceil(T / 32)
+  int chunk_tb;      // time blocks per work unit (a CTA keeps one bundle for a whole unit)
+  int* work_counter; // Snyder kernel: device counter for dynamic unit scheduling (zeroed per launch)
+  int knobs;         // experiments only (compiled in with -DCTB_EXPERIMENT): 1 = skip the copies, 4 = skip the reduction
+  // fused time reduction (ctb_aggregate_grouped): the launch covers days [t_off, t_off + T) of the
+  // groups' time axis; day t adds into output column tgroup[t_off + t]
+  const int32_t* tgroup;   // [T_total] non-decreasing, steps of 0 or 1; NULL = no time reduction
+  double* gpart;           // [n_out][R][g_ntb][gk] per-tile partial sums
+  int gk;                  // max output columns one 32-day tile touches
+  int g_ntb;               // 32-day tiles of the whole time axis
+  int t_off;               // multiple of 32
+  int n_groups;
+  const int32_t *g_t_lo, *g_t_hi;   // [n_groups] day range of every output column
+  int64_t scratch_ld;      // days per partial row of a split region (T, or T_total with time groups)
+  const int32_t *row_ptr, *col;
+  const double* w;
+  const int32_t *split_region, *split_slot_ptr;
+  int n_split;
+  CtbTr tr;
+};
+
+// One region x 32-day tile result (lane = day `t`, `valid` = t < T): normalise and store, or --
+// fused time reduction -- add the tile's days into per-tile partial sums per output column
+// (fixed shuffle tree: deterministic), or store the partial row of a split region.
+template <int NOUT>
+__device__ __forceinline__ void ctb_emit(const AggArgs& a, int target, double rden, const double (&v)[NOUT],
+                                         int lane, int t, bool valid, int tb, int tg, int tg0) {
+  if (target >= 0 && a.tgroup) {
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) {
+      const double val = v[j] * rden;
+      for (int k = 0; k < a.gk; ++k) {
+        double x = (tg == tg0 + k) ? val : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) a.gpart[(((size_t)j * a.R + target) * a.g_ntb + (a.t_off / CTB_TB + tb)) * a.gk + k] = x;
+      }
+    }
+  } else if (valid) {
+    if (target >= 0) {
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j)   // written once: leave L2 to the input
+        __stcs(&a.out[((size_t)j * a.R + target) * a.out_ld + t], v[j] * rden);
+    } else {
+      const int slot_o = ~target;
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) a.scratch[((size_t)j * a.n_scratch + slot_o) * a.scratch_ld + a.t_off + t] = v[j];
+    }
+  }
+}
+
+// ctb_stream.cu: the streaming kernel (IDENTITY / POLY, 16-byte aligned TIME_MAJOR planes)
+int ctb_launch_stream(const ctb_plan* P, const AggArgs& a, int dtype, int kind, int n_out, cudaStream_t st);
+
+// RAII: make the plan's device current for the duration of an entry point
+struct CtbDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit CtbDeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      switched = (err == cudaSuccess);
+    }
+  }
+  ~CtbDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 
 static inline int ctb_tr_nin(int kind) { return (kind == CTB_TR_EDD || kind == CTB_TR_GDD) ? 2 : 1; }
 

@@ -129,9 +129,11 @@ uint64_t hilbert_xy2d(uint32_t n, uint32_t x, uint32_t y) {
 struct BundleBuilder {
   std::vector<int64_t> b_blob_off{0};
   std::vector<int4> desc;
+  std::vector<int32_t> unit_tab;   // [n_bundles][CTB_TILE_UNITS]
   std::vector<uint8_t> blob;
   int32_t max_cells = 0, max_meta = 0, n_segments = 0;
   int64_t n_pieces_total = 0;
+  int64_t n_quads = 0, n_quads_conflict = 0;
   int32_t bytes_cd = 4;       // staged bytes per cell-day
   int32_t elem_bytes = 4;     // element size of the staged inputs
   int32_t tile_cap = 0;       // bytes of one staging tile
@@ -149,11 +151,12 @@ struct BundleBuilder {
     return (int32_t)sizeof(CtbBlobHeader) + pad(n_pieces * 4, 16);
   }
   static int32_t part_b_bytes(int32_t n_seg, int32_t n_ent_pad) {
-    return n_seg * (int32_t)sizeof(CtbSeg) + 12 * pad(n_ent_pad, 8);
+    return n_seg * (int32_t)sizeof(CtbSeg) + n_ent_pad * (int32_t)sizeof(CtbEnt);
   }
   int32_t tile_bytes(int32_t n_pieces) const { return n_pieces * CTB_PIECE * CTB_S * bytes_cd; }
   bool fits_counts(int32_t n_pieces, int32_t n_seg, int32_t n_ent_pad) const {
     return tile_bytes(n_pieces) <= tile_cap && part_a_bytes(n_pieces) <= CTB_META_A_CAP &&
+           n_pieces * CTB_PIECE * elem_bytes <= CTB_TILE_UNITS * 16 &&
            part_b_bytes(n_seg, n_ent_pad) <= meta_cap &&
            n_pieces * CTB_PIECE <= 65532 && n_ent_pad <= 65532 * 4;
   }
@@ -175,14 +178,13 @@ struct BundleBuilder {
                      [](const Seg& a, const Seg& b) { return a.cols.size() > b.cols.size(); });
     const int32_t n_seg = (int32_t)cur_segs.size();
     const int32_t n_p = (int32_t)cur_pieces.size();
-    const int32_t n_ent_pad = pad(cur_ent_pad, 8);
+    const int32_t n_ent_pad = cur_ent_pad;
     CtbBlobHeader h{};
     h.n_pieces = n_p; h.n_seg = n_seg; h.n_ent_pad = n_ent_pad;
     h.off_seg = 0;
-    h.off_w = n_seg * (int32_t)sizeof(CtbSeg);
-    h.off_loc = h.off_w + 8 * n_ent_pad;
+    h.off_ent = n_seg * (int32_t)sizeof(CtbSeg);
     h.bytes_a = part_a_bytes(n_p);
-    h.bytes_b = pad(h.off_loc + 4 * n_ent_pad, 16);
+    h.bytes_b = pad(h.off_ent + n_ent_pad * (int32_t)sizeof(CtbEnt), 16);
     const size_t base = blob.size();
     const size_t bytes = (size_t)h.bytes_a + h.bytes_b;
     blob.resize(base + bytes, 0);
@@ -190,22 +192,81 @@ struct BundleBuilder {
     std::memcpy(&blob[base + sizeof h], cur_pieces.data(), (size_t)n_p * 4);
     const size_t bb = base + h.bytes_a;
     CtbSeg* segs = reinterpret_cast<CtbSeg*>(&blob[bb + h.off_seg]);
-    double* w = reinterpret_cast<double*>(&blob[bb + h.off_w]);
-    uint32_t* loc = reinterpret_cast<uint32_t*>(&blob[bb + h.off_loc]);
-    desc.push_back(make_int4((int)(base & 0xffffffffu), (int)(base >> 32), h.bytes_a, h.bytes_b));
+    CtbEnt* ent = reinterpret_cast<CtbEnt*>(&blob[bb + h.off_ent]);
+    // staged 16-byte units of a day plane: (piece, half) -> element offset of the unit
+    const int32_t halves = elem_bytes / 4, cpu = 16 / elem_bytes;
+    const int32_t n_units = n_p * halves;
+    desc.push_back(make_int4((int)(base & 0xffffffffu), (int)(base >> 32), (int)bytes, n_units));
+    const size_t ut = unit_tab.size();
+    unit_tab.resize(ut + CTB_TILE_UNITS, 0);
+    for (int32_t u = 0; u < n_units; ++u)
+      unit_tab[ut + u] = cur_pieces[u / halves] * CTB_PIECE + (u % halves) * cpu;
     int32_t e = 0;
+    std::vector<int32_t> colq;     // staged column of every entry of the segment
+    std::vector<int32_t> order;
     for (int32_t i = 0; i < n_seg; ++i) {
       const Seg& s = cur_segs[i];
-      segs[i] = CtbSeg{s.target, (uint16_t)(e / 4), (uint16_t)s.cols.size(),
+      const int32_t n = (int32_t)s.cols.size();
+      segs[i] = CtbSeg{s.target, (uint16_t)(e / 4), (uint16_t)n,
                        s.target >= 0 ? 1.0 / den[s.target] : 1.0};
-      for (size_t k = 0; k < s.cols.size(); ++k) {
+      colq.resize(n);
+      for (int32_t k = 0; k < n; ++k) {
         const int32_t piece = s.cols[k] / CTB_PIECE;
         const int32_t lp = (int32_t)(std::lower_bound(cur_pieces.begin(), cur_pieces.end(), piece) -
                                      cur_pieces.begin());
-        loc[e + k] = (uint32_t)(lp * CTB_PIECE + s.cols[k] % CTB_PIECE) * (uint32_t)(CTB_S * elem_bytes);
-        w[e + k] = s.ws[k];
+        colq[k] = lp * CTB_PIECE + s.cols[k] % CTB_PIECE;
       }
-      e += pad((int32_t)s.cols.size(), 4);
+      // quads: no two entries of one residue class (column mod 4) in a quad while the classes
+      // allow it.  Classes in descending size; a class spreads its entries over the quads that
+      // are emptiest so far (fill levels stay within one of each other, so no quad overflows
+      // before all are full); a class with more entries than quads doubles up (2-way conflict).
+      const int32_t nq = (n + 3) / 4;
+      std::vector<int32_t> bucket[4];
+      for (int32_t k = 0; k < n; ++k) bucket[colq[k] & 3].push_back(k);
+      int32_t cls[4] = {0, 1, 2, 3};
+      std::stable_sort(cls, cls + 4, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+      std::vector<std::vector<int32_t>> quad(nq);
+      std::vector<int32_t> qorder(nq);
+      for (int c = 0; c < 4; ++c) {
+        const std::vector<int32_t>& bk = bucket[cls[c]];
+        size_t next = 0;
+        while (next < bk.size()) {
+          // one pass: at most one entry of this class per quad, emptiest quads first
+          std::iota(qorder.begin(), qorder.end(), 0);
+          std::stable_sort(qorder.begin(), qorder.end(),
+                           [&](int a, int b) { return quad[a].size() < quad[b].size(); });
+          bool placed = false;
+          for (int32_t qi = 0; qi < nq && next < bk.size(); ++qi) {
+            std::vector<int32_t>& q = quad[qorder[qi]];
+            // the last quad holds n - 4 (nq - 1) entries
+            const size_t cap = (qorder[qi] == nq - 1) ? (size_t)(n - 4 * (nq - 1)) : 4;
+            if (q.size() < cap) { q.push_back(bk[next++]); placed = true; }
+          }
+          if (!placed) break;   // cannot happen: total capacity == n
+        }
+      }
+      order.clear();
+      for (int32_t q = 0; q < nq; ++q) {
+        std::stable_sort(quad[q].begin(), quad[q].end(), [&](int a, int b) { return (colq[a] & 3) < (colq[b] & 3); });
+        bool conflict = false;
+        for (size_t k = 1; k < quad[q].size(); ++k)
+          conflict |= ((colq[quad[q][k]] & 3) == (colq[quad[q][k - 1]] & 3));
+        for (int32_t k : quad[q]) order.push_back(k);
+        ++n_quads;
+        if (conflict) ++n_quads_conflict;
+      }
+      for (int32_t k = 0; k < n; ++k) {
+        ent[e + k].w = s.ws[order[k]];
+        ent[e + k].off = (uint32_t)colq[order[k]] * (uint32_t)elem_bytes;
+      }
+      // padding of the last quad: weight 0 on a copy of the quad's first entry -- the same shared
+      // address (a broadcast, no bank conflict) and a value of the region's own (a NaN elsewhere in
+      // the tile must not send this region to the checked loop)
+      for (int32_t k = n; k < pad(n, 4); ++k) {
+        ent[e + k].w = 0.0;
+        ent[e + k].off = ent[e + (n & ~3)].off;
+      }
+      e += pad(n, 4);
     }
     b_blob_off.push_back((int64_t)blob.size());
     n_segments += n_seg;
@@ -234,7 +295,7 @@ extern "C" void ctb_plan_free(ctb_plan* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->d_row_cell); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_w);
-  cudaFree(p->d_den); cudaFree(p->d_b_blob_off); cudaFree(p->d_b_desc); cudaFree(p->d_work_counter);
+  cudaFree(p->d_den); cudaFree(p->d_b_blob_off); cudaFree(p->d_b_desc); cudaFree(p->d_unit_tab); cudaFree(p->d_work_counter);
   cudaFree(p->d_blob); cudaFree(p->d_split_region); cudaFree(p->d_split_slot_ptr);
   cudaSetDevice(prev);
   delete p;
@@ -455,6 +516,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   B.bytes_cd = bytes_cd;
   B.elem_bytes = opts && opts->elem_bytes == 8 ? 8 : 4;
   P->elem_bytes = B.elem_bytes;
+  P->stage_bytes = bytes_cd;
   B.tile_cap = tile_cap;
   B.meta_cap = meta_cap;
   B.den = P->h_den.data();
@@ -579,7 +641,10 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   if ((rc = upload(&P->d_b_blob_off, B.b_blob_off))) return rc;
   if ((rc = upload(&P->d_blob, B.blob))) return rc;
   if ((rc = upload(&P->d_b_desc, B.desc))) return rc;
-  CTB_CUDA(cudaMalloc((void**)&P->d_work_counter, CTB_N_WORK_COUNTERS * sizeof(int)));
+  if ((rc = upload(&P->d_unit_tab, B.unit_tab))) return rc;
+  // [0, N): Snyder kernel (zeroed per launch); [N, 2N): streaming kernel's self-re-arming pairs
+  CTB_CUDA(cudaMalloc((void**)&P->d_work_counter, 2 * CTB_N_WORK_COUNTERS * sizeof(int)));
+  CTB_CUDA(cudaMemset(P->d_work_counter, 0, 2 * CTB_N_WORK_COUNTERS * sizeof(int)));
   if ((rc = upload(&P->d_split_region, split_region))) return rc;
   if ((rc = upload(&P->d_split_slot_ptr, split_slot_ptr))) return rc;
   P->n_bundles = (int32_t)B.b_blob_off.size() - 1;
@@ -595,6 +660,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   I.max_meta_bytes = B.max_meta;
   I.n_packed_cells = P->compact ? (int32_t)plan_ncell : 0;
   I.time_block = CTB_TB; I.max_region_rows = max_rows;
+  I.n_quads = B.n_quads; I.n_quads_conflict = B.n_quads_conflict;
   CTB_CUDA(cudaDeviceSynchronize());
   return CTB_OK;
 }
@@ -672,8 +738,10 @@ extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_
   n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(T, 1));
   const char* src = static_cast<const char*>(x);
   char* out = static_cast<char*>(dst);
-  const bool nt = (reinterpret_cast<uintptr_t>(dst) & 63) == 0 && ((size_t)packed * es) % 64 == 0 &&
-                  !(getenv("CTB_PACK_NT") && atoi(getenv("CTB_PACK_NT")) == 0);
+  const bool nt = (reinterpret_cast<uintptr_t>(dst) & 63) == 0 && ((size_t)packed * es) % 64 == 0;
+  // the last piece of a grid whose cell count is not a multiple of 4 ends past the plane: copy
+  // what exists, zero-fill the rest (never read past the caller's buffer)
+  const size_t plane_bytes = (size_t)P->nlat_phys * (size_t)P->nlon_phys * es;
   auto work = [&](int64_t d0, int64_t d1) {
     for (int64_t d = d0; d < d1; ++d) {
       const int64_t tp = time_index ? time_index[t_begin + d] : t_begin + d;
@@ -681,8 +749,16 @@ extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_
       char* o = out + (size_t)d * packed * es;
       for (const auto& r : P->h_pack_runs) {
         char* q = o + (size_t)r.packed_piece * piece_bytes;
-        const char* s = plane + (size_t)r.phys_piece * piece_bytes;
+        const size_t s_off = (size_t)r.phys_piece * piece_bytes;
+        const char* s = plane + s_off;
         const size_t n = (size_t)r.n_pieces * piece_bytes;
+        if (s_off + n > plane_bytes) {   // ragged tail of the plane (at most one run per day)
+          const size_t have = plane_bytes > s_off ? plane_bytes - s_off : 0;
+          std::memcpy(q, s, have);
+          std::memset(q + have, 0, n - have);
+          if (nt) std::memset(q + n, 0, (64 - (n & 63)) & 63);
+          continue;
+        }
 #if defined(__SSE2__)
         if (nt) {
           // runs start on 64-byte boundaries of the packed plane: write whole lines (the run, then

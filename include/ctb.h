@@ -68,8 +68,8 @@ typedef struct ctb_plan ctb_plan;
 typedef struct ctb_plan_opts {
   int32_t stage_bytes_per_cell_day; /* bytes one gridcell-day occupies in the staging
                                        tile: n_in * sizeof(elem); default 4 (one f32) */
-  int32_t smem_budget_bytes;        /* staging shared memory per CTA; default 72 KiB
-                                       (three CTAs per SM) */
+  int32_t smem_budget_bytes;        /* cap on one staging tile in bytes (tests use it to force
+                                       region splitting); default: 128 16-byte units per day */
   int32_t compact;                  /* 1: the plan addresses a PACKED input [T][n_packed_cells]
                                        holding only the referenced 4-cell pieces (what
                                        ctb_host_pack writes) instead of the full grid */
@@ -95,6 +95,8 @@ typedef struct ctb_plan_info {
   int32_t max_region_rows; /* largest region, in kept rows */
   int32_t max_meta_bytes;  /* largest per-bundle metadata blob + piece list, bytes */
   int32_t n_packed_cells;  /* compact plans: cells per packed plane (4 * distinct pieces), else 0 */
+  int64_t n_quads;         /* 4-entry groups the streaming kernel reduces per 32-day tile */
+  int64_t n_quads_conflict;/* ... of which hold two columns of one residue class (2-way bank conflict) */
 } ctb_plan_info;
 
 /* ---- misc ---------------------------------------------------------------- */
@@ -149,8 +151,8 @@ int ctb_plan_row_weights(const ctb_plan* plan, double* w_out /*[n_rows]*/);
  *                  A time-chunked caller passes out + t0 with out_ld = total T.
  *  workspace     : DEVICE scratch of ctb_aggregate_workspace_bytes() bytes (may be
  *                  NULL when that is 0)
- *  variant       : 0 = auto; 1 = fused staged kernel (TIME_MAJOR only); 2 = direct
- *                  warp-per-region kernel.  | 0x100: x0/x1 are MAPPED PINNED HOST memory read
+ *  variant       : 0 = auto; 1 = staged (TIME_MAJOR only: the streaming kernel for IDENTITY /
+ *                  POLY, the Snyder kernel for EDD / GDD); 2 = direct warp-per-region kernel.  | 0x100: x0/x1 are MAPPED PINNED HOST memory read
  *                  in place over PCIe (zero-copy: only the referenced gridcells cross the bus)
  */
 size_t ctb_aggregate_workspace_bytes(const ctb_plan* plan, int64_t T, int n_out);
@@ -177,17 +179,30 @@ int ctb_gather_rows(const ctb_plan* plan, const void* x, int dtype, int layout, 
 int ctb_host_pack(const ctb_plan* plan, const void* x, int dtype, int64_t stride,
                   const int64_t* time_index, int64_t t_begin, int64_t T, void* dst, int n_threads);
 
-/* ---- diagnostics ---------------------------------------------------------- *
- * Loads-only replay of the staging traffic of ctb_aggregate (TIME_MAJOR, f32) on the
- * plan's real footprint; used by bench_micro/ to measure what the memory system delivers
- * for a lane mapping (lanes_p pieces x 32/lanes_p days per warp), `unroll` loads in
- * flight per thread, `warps` per CTA and `ctas_per_sm`.  `sink` is a 4-byte DEVICE word. */
-int ctb_debug_stage_bw(const ctb_plan* plan, const void* x, int64_t stride, int64_t T, int lanes_p,
-                       int unroll, int warps, int ctas_per_sm, void* sink, void* stream);
-/* Same traffic staged with cp.async copies of `width` bytes (4, 8, 16) straight into
- * transposed shared-memory tiles, `nbuf` tile buffers in flight, `loader_warps` issuing. */
-int ctb_debug_cpasync_bw(const ctb_plan* plan, const void* x, int64_t stride, int64_t T, int width,
-                         int loader_warps, int nbuf, void* stream);
+/* ---- fused time reduction (annual sums of the daily region values) -------- *
+ * The step after the path in CIL pipelines: EDD_P = sum over the days of a period of the
+ * aggregated EDD_d (transformations.py:17-21).  group_of_day (HOST int32[T]) gives the output
+ * column of every day: it starts at 0 and grows by 0 or 1 per day (contiguous periods, e.g. year
+ * index).  ctb_aggregate_grouped writes out[(j*R + r)*out_ld + g] = sum over the days t of column
+ * g of the value ctb_aggregate would have written to out[..][t] -- the region x time block never
+ * reaches memory, the output is n_days/n_groups times smaller.  Summation order is fixed
+ * (deterministic); NaN and infinities propagate like in a plain sum.
+ * A time-chunked caller (host inputs that arrive in pieces) passes the window: the T input days
+ * are days [t_begin, t_begin + T) of the groups' time axis (t_begin a multiple of 32, time_index
+ * relative to the window's inputs), with flush = 0 for all but the last call; the call with
+ * flush != 0 (T may be 0) finishes the sums and writes `out`.  All calls share one workspace
+ * (split-region rows + per-tile partial sums) and one stream. */
+typedef struct ctb_time_groups ctb_time_groups;
+int ctb_time_groups_create(const int32_t* group_of_day, int64_t T, int device, ctb_time_groups** out);
+void ctb_time_groups_free(ctb_time_groups* groups);
+int32_t ctb_time_groups_count(const ctb_time_groups* groups);
+size_t ctb_aggregate_grouped_workspace_bytes(const ctb_plan* plan, const ctb_time_groups* groups, int n_out);
+int ctb_aggregate_grouped(const ctb_plan* plan, const void* x0, const void* x1, int dtype, int layout,
+                          int64_t stride, const int32_t* time_index, int64_t T, int transform,
+                          const double* params, int n_params, int n_out, const ctb_time_groups* groups,
+                          int64_t t_begin, int flush,
+                          double* out /*[n_out][R][out_ld >= n_groups]*/, int64_t out_ld, void* workspace,
+                          size_t workspace_bytes, int variant, void* stream);
 
 #ifdef __cplusplus
 }

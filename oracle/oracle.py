@@ -45,6 +45,7 @@ import numpy as np
 import pandas as pd
 
 __all__ = [
+    "time_group_sum",
     "convert_lons_mono",
     "convert_lons_split",
     "leap_day_keep_mask",
@@ -266,3 +267,25 @@ def tas_poly(tas, times, power, time_axis=0):
         raise ValueError
     out = (tas - 273.15) ** power
     return out, tas_poly_time_labels(np.asarray(times)[keep])
+
+
+# ---------------------------------------------------------------------------
+# temporal sums after the aggregation
+# ---------------------------------------------------------------------------
+def time_group_sum(values, dims, labels, time_dim="time"):
+    """Sum of the daily region values over runs of equal ``labels`` along ``time_dim`` -- what
+    ``out.groupby(label).sum()`` gives for period labels that are runs of consecutive steps
+    (``EDD_P = sum_d EDD_d``, /root/reference/climate_toolbox/transformations/transformations.py:17-21).
+    A plain sum: NaN and infinities propagate.  Returns (array, unique labels in order)."""
+    values = np.asarray(values, dtype=np.float64)
+    labels = np.asarray(labels)
+    ax = list(dims).index(time_dim)
+    n = values.shape[ax]
+    assert len(labels) == n
+    change = np.ones(n, dtype=bool)
+    change[1:] = labels[1:] != labels[:-1]
+    starts = np.flatnonzero(change)
+    ends = np.r_[starts[1:], n]
+    parts = [np.take(values, np.arange(a, b), axis=ax).sum(axis=ax, keepdims=True) for a, b in zip(starts, ends)]
+    out = np.concatenate(parts, axis=ax) if parts else np.take(values, [], axis=ax)
+    return out, labels[change]

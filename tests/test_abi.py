@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_struct_layouts_match_header(built):
     # sizes follow from the field lists in include/ctb.h
     assert ctypes.sizeof(_native.PlanOpts) == 32
-    assert ctypes.sizeof(_native.PlanInfo) == 4 * 8 + 2 * 4 + 2 * 8 + 8 * 4
+    assert ctypes.sizeof(_native.PlanInfo) == 4 * 8 + 2 * 4 + 2 * 8 + 8 * 4 + 2 * 8
 
 
 def test_invalid_calls_fail_cleanly_without_gpu(built):

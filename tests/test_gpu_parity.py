@@ -153,9 +153,20 @@ def test_label_miss_raises_keyerror(clim_data, ref_fix):
 # ----------------------------------------------------------------------------
 # synthetic configs at oracle-friendly sizes
 # ----------------------------------------------------------------------------
+_TABLES = {}
+
+
+def _table(d, R, seed=1234):
+    """Synthetic weights tables are deterministic and slow to build at 0.25 degree: one per session."""
+    key = (d, R, seed)
+    if key not in _TABLES:
+        _TABLES[key] = synthetic.weights_table(d, R, seed=seed)
+    return _TABLES[key]
+
+
 def _config(d, R, T, seed=1234, nan_frac=0.001, lon_0_360=False, dtype=np.float32):
     lat, lon = synthetic.grid_labels(d, lon_0_360=lon_0_360)
-    df = synthetic.weights_table(d, R, seed=seed)
+    df = _table(d, R, seed)
     tas, tmin, tmax = synthetic.tas_field(T, len(lat), len(lon), seed=7, nan_frac=nan_frac, dtype=dtype)
     return lat, lon, df, tas, tmin, tmax
 
@@ -520,6 +531,198 @@ def test_prepare_spatial_weights_data_csv(tmp_path):
 
 
 # ----------------------------------------------------------------------------
+# BASELINE.json configs 3, 4, 5 and the multi-weight pass AT THEIR OWN SHAPE
+# (0.25 degree, 24,378 regions, 866+ bundles), a few days against the oracle
+# ----------------------------------------------------------------------------
+def _put(a, where):
+    return a if where == "host" else torch.from_numpy(a).cuda()
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_config3_shape_poly_orders_quarter_degree(where):
+    """Config 3: tas_poly orders 1-4 fused, 0.25 degree -> 24,378 regions, popwt."""
+    lat, lon, df, tas, _, _ = _config(0.25, 24378, 4)
+    time = pd.date_range("2001-03-01", periods=4)
+    ds = Dataset({"tas": (("time", "lat", "lon"), _put(tas, where))},
+                 coords={"time": time, "lat": lat, "lon": lon})
+    names = ["tas", "tas-poly-2", "tas-poly-3", "tas-poly-4"]
+    out = weighted_aggregate_grid_to_regions(tas_poly(ds, [1, 2, 3, 4], names), names, "popwt", "hierid", weights=df)
+    for p, name in zip((1, 2, 3, 4), names):
+        xt, _ = oracle.tas_poly(tas, time, p)
+        ref, rd, labels, scale = oracle_agg(xt, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+        assert out[name].dims == rd and out[name].shape == (4, 24378)
+        check(out[name].values, ref, scale)
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_config4_shape_snyder_cropwt_quarter_degree(where):
+    """Config 4: Snyder EDD at two thresholds + GDD from (tasmin, tasmax), cropwt (60 % of the
+    rows fall back to areawt), 0.25 degree -> 24,378 regions."""
+    lat, lon, df, _, tmin, tmax = _config(0.25, 24378, 3)
+    dims = ("time", "lat", "lon")
+    coords = {"time": np.arange(3), "lat": lat, "lon": lon}
+    tn = DataArray(_put(tmin, where), dims=dims, coords=coords, attrs={"units": "K"})
+    tx = DataArray(_put(tmax, where), dims=dims, coords=coords, attrs={"units": "K"})
+    ds = Dataset(coords=coords)
+    ds["edd10"] = snyder_edd(tn, tx, 283.15)
+    ds["edd30"] = snyder_edd(tn, tx, 303.15)
+    ds["gdd"] = snyder_gdd(tn, tx, 283.15, 303.15)
+    out = weighted_aggregate_grid_to_regions(ds, ["edd10", "edd30", "gdd"], "cropwt", "hierid", weights=df)
+    W = np.nan_to_num((tmax.astype(np.float64) - tmin) / 2)      # magnitude of the terms that cancel
+    for name, f in (("edd10", oracle.snyder_edd(tmin, tmax, 283.15)), ("edd30", oracle.snyder_edd(tmin, tmax, 303.15)),
+                    ("gdd", oracle.snyder_gdd(tmin, tmax, 283.15, 303.15))):
+        ref, rd, labels, scale = oracle_agg(f, dims, lat, lon, df, "cropwt", "hierid")
+        scale_w = oracle.weighted_aggregate_grid_to_regions(W, dims, lat, lon, df, "cropwt", "hierid")[0]
+        assert out[name].shape == (3, 24378)
+        check(out[name].values, ref, scale + scale_w)
+
+
+def test_several_weight_columns_quarter_degree():
+    """popwt + areawt + cropwt from ONE pass at 0.25 degree == three oracle passes."""
+    lat, lon, df, tas, _, _ = _config(0.25, 24378, 3)
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": np.arange(3), "lat": lat, "lon": lon})
+    cols = ["popwt", "areawt", "cropwt"]
+    out = weighted_aggregate_grid_to_regions_multi(ds, "tas", cols, "hierid", df)
+    for c in cols:
+        ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, c, "hierid")
+        assert out["tas_" + c].dims == rd and list(out.hierid.values) == list(labels)
+        check(out["tas_" + c].values, ref, scale)
+
+
+def test_config5_slice_model_years_through_a_buffer_pool():
+    """Config 5 (ensemble streaming): model-years from a pool of resident buffers through ONE plan and
+    one reused output buffer, as bench.py --workload config5 does -- every model-year's output is
+    compared (3 days of each against the oracle, all of it against the direct kernel)."""
+    T = 64
+    lat, lon, df, _, _, _ = _config(0.25, 24378, 1)
+    plan = E.get_plan(E.GridSpec(lat, lon), df, "popwt", "hierid")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    pool = [288.0 + 10.0 * torch.randn((T, len(lat) * len(lon)), generator=g, device="cuda", dtype=torch.float32)
+            for _ in range(2)]
+    out = torch.empty((1, plan.R, T), dtype=torch.float64, device="cuda")
+    ok = torch.from_numpy(plan.den() > 0).cuda()
+    for y in range(4):                                   # 4 model-years through 2 buffers
+        x = pool[y % 2]
+        if y >= 2:
+            x.add_(1.0)                                  # the "next model-year" lands in the same buffer
+        E.aggregate_device(plan, x, None, N.LAYOUT_TIME_MAJOR, x.shape[1], None, T, out=out)
+        direct = E.aggregate_device(plan, x, None, N.LAYOUT_TIME_MAJOR, x.shape[1], None, T,
+                                    variant=N.VARIANT_DIRECT)
+        assert torch.allclose(out[0][ok], direct[0][ok], rtol=1e-12, atol=0)
+        days = [0, 31, 63]
+        sl = x[days].cpu().numpy().reshape(3, len(lat), len(lon))
+        ref, rd, labels, scale = oracle_agg(sl, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+        check(out[0][:, days].cpu().numpy().T, ref, scale)
+
+
+# ----------------------------------------------------------------------------
+# plan cache: in-place edits of the weights frame must rebuild the plan
+# ----------------------------------------------------------------------------
+def test_plan_cache_sees_in_place_edits_of_the_weights_frame():
+    lat, lon, df, tas, _, _ = _config(1.0, 800, 6)
+    df = df.copy()
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": np.arange(6), "lat": lat, "lon": lon})
+
+    def both():
+        out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=df)
+        ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+        assert list(out.hierid.values) == list(labels)
+        check(out.tas.values, ref, scale)
+        return out.tas.values
+
+    a = both()
+    # (1) region labels edited in the MIDDLE of the frame, in place (first and last row untouched)
+    mid = df.index[len(df) // 3: len(df) // 3 + 200]
+    df.loc[mid, "hierid"] = df["hierid"].values[0]
+    b = both()
+    assert not np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+    # (2) one weight column reversed in place: same multiset of values, other positions
+    df["popwt"] = df["popwt"].values[::-1].copy()
+    both()
+    # (3) two rows' weights swapped
+    i, j = df.index[10], df.index[500]
+    wi, wj = df.loc[i, "areawt"], df.loc[j, "areawt"]
+    df.loc[i, "areawt"], df.loc[j, "areawt"] = wj, wi
+    both()
+    # the multi-weight entry point keeps its own stacked frame: same hazard
+    m1 = weighted_aggregate_grid_to_regions_multi(ds, "tas", ["popwt", "areawt"], "hierid", df)
+    df.loc[mid, "hierid"] = df["hierid"].values[-1]
+    m2 = weighted_aggregate_grid_to_regions_multi(ds, "tas", ["popwt", "areawt"], "hierid", df)
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "areawt", "hierid")
+    check(m2["tas_areawt"].values, ref, scale)
+    assert m1["tas_areawt"].shape[1] != m2["tas_areawt"].shape[1] or not np.array_equal(
+        np.nan_to_num(m1["tas_areawt"].values), np.nan_to_num(m2["tas_areawt"].values))
+
+
+def test_back_to_back_host_calls_do_not_share_staging():
+    """Two host-input calls with different data and keep_on_device=True: the second call packs into
+    the pinned staging buffers the first call's last H2D copies may still be reading."""
+    lat, lon, df, tas, _, _ = _config(1.0, 3000, 96, nan_frac=0.0)
+    mk = lambda a: Dataset({"tas": (("time", "lat", "lon"), a)},
+                           coords={"time": np.arange(a.shape[0]), "lat": lat, "lon": lon})
+    tas2 = (tas + 7.0).astype(np.float32)
+    refs = [oracle_agg(a, ("time", "lat", "lon"), lat, lon, df, "areawt", "hierid") for a in (tas, tas2)]
+    for _ in range(3):
+        r1 = weighted_aggregate_grid_to_regions(mk(tas), "tas", "areawt", "hierid", weights=df, keep_on_device=True)
+        r2 = weighted_aggregate_grid_to_regions(mk(tas2), "tas", "areawt", "hierid", weights=df, keep_on_device=True)
+        torch.cuda.synchronize()
+        for r, (ref, rd, labels, scale) in zip((r1, r2), refs):
+            check(r["tas"].data.cpu().numpy(), ref, scale)
+
+
+# ----------------------------------------------------------------------------
+# fused time reduction (SURVEY 8-f4): annual sums inside the kernel
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("kind", ["identity", "edd", "cell_major"])
+def test_time_groups_annual_sums(where, kind):
+    """time_groups='year' == groupby(year).sum() of the daily result; years of 365 days do not align
+    with the 32-day tiles, 800 days of host input arrive in several chunks."""
+    lat, lon, df, tas, tmin, tmax = _config(1.0, 3000, 800)
+    time = pd.date_range("2001-01-01", periods=800)
+    dims = ("time", "lat", "lon")
+    coords = {"time": time, "lat": lat, "lon": lon}
+    if kind == "edd":
+        tn = DataArray(_put(tmin, where), dims=dims, coords=coords, attrs={"units": "K"})
+        tx = DataArray(_put(tmax, where), dims=dims, coords=coords, attrs={"units": "K"})
+        ds = Dataset(coords=coords)
+        ds["v"] = snyder_edd(tn, tx, 288.15)
+        f = oracle.snyder_edd(tmin, tmax, 288.15)
+        fdims = dims
+    elif kind == "cell_major":
+        fdims = ("lat", "lon", "time")
+        f = np.ascontiguousarray(tas.transpose(1, 2, 0))
+        ds = Dataset({"v": (fdims, _put(f, where))}, coords=coords)
+    else:
+        ds = Dataset({"v": (dims, _put(tas, where))}, coords=coords)
+        f, fdims = tas, dims
+    out = weighted_aggregate_grid_to_regions(ds, "v", "popwt", "hierid", weights=df, time_groups="year")
+    ref, rd, labels, scale = oracle_agg(f, fdims, lat, lon, df, "popwt", "hierid")
+    ref_y, years = oracle.time_group_sum(ref, rd, time.year.values)
+    scale_y, _ = oracle.time_group_sum(np.nan_to_num(scale), rd, time.year.values)
+    assert out.v.dims == rd and list(out.time.values) == list(years) == [2001, 2002, 2003]
+    check(out.v.values, ref_y, scale_y)
+
+
+def test_time_groups_blocks_and_split_regions():
+    """Block-length groups shorter than a tile (several groups per 32-day tile) and regions split
+    over bundles (partial rows reduced by the fix-up kernel)."""
+    lat, lon, df, tas, _, _ = _config(1.0, 40, 75)
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": np.arange(75), "lat": lat, "lon": lon})
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+    for p, budget in ((7, 0), (10, 8 * 1024), (75, 0), (1, 0)):
+        out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=df, time_groups=p,
+                                                 smem_budget=budget)
+        ref_g, gl = oracle.time_group_sum(ref, rd, np.arange(75) // p)
+        scale_g, _ = oracle.time_group_sum(np.nan_to_num(scale), rd, np.arange(75) // p)
+        assert out.tas.shape == ref_g.shape
+        check(out.tas.values, ref_g, scale_g)
+
+
+# ----------------------------------------------------------------------------
 # full size (BASELINE.json configs[1]): size-independent properties
 # ----------------------------------------------------------------------------
 def test_full_size_properties():
@@ -528,7 +731,7 @@ def test_full_size_properties():
     direct kernels agree; (d) a 3-day slice matches the oracle."""
     d, R, T = 0.25, 24378, 365
     lat, lon = synthetic.grid_labels(d)
-    df = synthetic.weights_table(d, R)
+    df = _table(d, R)
     g = torch.Generator(device="cuda").manual_seed(7)
     x = 288.0 + 10.0 * torch.randn((T, len(lat), len(lon)), generator=g, device="cuda", dtype=torch.float32)
     coords = {"time": np.arange(T), "lat": lat, "lon": lon}
