@@ -2,13 +2,16 @@
 """Benchmark of the grid->region aggregation hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload config2|config3|config4|config1|config5]
+                    [--workload config2|config3|config4|config1|config5] [--no-also]
 
 One "step" = one pass of the hot path over one synthetic batch of the workload
 (config2: 4 x 365 days of 0.25-degree tas [1460][720][1440] f32 -> 24,378 regions, popwt).
-N > 1 (torchrun, one rank per GPU): every rank aggregates its OWN batch (another
-GCM / scenario / block of years) with the plan replicated -- weak scaling, no data-path
-collective.  Prints ONE JSON line on rank 0.
+N > 1 (torchrun, one rank per GPU): `value` is weak scaling -- every rank aggregates its OWN batch
+(another GCM / scenario / block of years) with the plan replicated, no data-path collective; the
+`strong` block of the same line times what north_star describes: ONE 1460-day batch sharded along
+time over the ranks, compute + the final NCCL gather of the region x time outputs (overlapped).
+Prints ONE JSON line on rank 0.  `also` (N = 1) carries device-timed lines of the other
+BASELINE.json configs and of input variants (NaN over the ocean, annual sums).
 """
 from __future__ import annotations
 
@@ -32,16 +35,23 @@ WORKLOADS = {
                 "BCSD-shaped 0.25deg daily tas 4x365x720x1440 f32 -> 24,378 hierid regions, popwt"),
     "config3": (0.25, 24378, 1460, "popwt", "poly", 1, 4,
                 "fused tas_poly orders 1-4 + aggregation, 0.25deg 1460 days -> 24,378 regions, popwt"),
-    "config4": (0.25, 24378, 730, "cropwt", "edd", 2, 2,
-                "fused Snyder EDD (2 thresholds) from tasmin/tasmax, 0.25deg 730 days -> 24,378 regions, cropwt"),
+    "config4": (0.25, 24378, 1460, "cropwt", "edd", 2, 2,
+                "fused Snyder EDD (2 thresholds) from tasmin/tasmax, 0.25deg 1460 days -> 24,378 regions, cropwt"),
     # CMIP5-ensemble scale (21 GCMs x 2 RCPs x 95 years = 3,990 model-years): one step streams a
     # slice of YEARS_PER_STEP model-years through a pool of POOL resident year buffers
     "config5": (0.25, 24378, 365, "popwt", "identity", 1, 1,
                 "ensemble streaming: model-years of 365x720x1440 f32 -> 24,378 regions, popwt; "
-                "8 model-years per step from a pool of 4 resident buffers (full job: 3,990 model-years)"),
+                "8 model-years per step and rank from a pool of 4 resident buffers (full job: 3,990 model-years, "
+                "model-years dealt round-robin to the ranks)"),
 }
 YEARS_PER_STEP, POOL, ENSEMBLE_YEARS = 8, 4, 21 * 2 * 95
 METRIC = "region-days/sec"
+PARAMS = {"identity": (), "poly": (273.15, 1, 2, 3, 4), "edd": (283.15, 303.15)}
+KERNEL = {"identity": "agg_stream_kernel", "poly": "agg_stream_kernel", "edd": "agg_snyder_kernel"}
+# fp64-pipe instructions per CSR entry and day of the Snyder kernel (2 thresholds), counted in the SASS of
+# agg_snyder_kernel<float, EDD, 2> (profiles/r2_sass_histograms.md); 64 fp64 lanes per SM and clock
+SNYDER_FP64_OPS_PER_ENTRY_DAY = 118
+FP64_LANES_PER_SM_CLK = 64
 
 
 def _peaks():
@@ -49,6 +59,16 @@ def _peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def config_dict(workload, T, world):
+    """The `config` object: the same keys and values in both arms (the driver compares them)."""
+    deg, R, _, aggwt, kind, n_in, n_out, desc = WORKLOADS[workload]
+    nlat, nlon = int(round(180 / deg)), int(round(360 / deg))
+    return {"workload": desc, "T": T, "grid": [nlat, nlon], "regions": R, "aggwt": aggwt,
+            "input_dtype": "f32", "accumulate": "f64", "n_in": n_in, "n_out": n_out,
+            "l2": "inputs larger than L2 ({:.2f} GB per step)".format(n_in * T * nlat * nlon * 4 / 1e9),
+            "per_rank": "own batch, plan replicated, outputs stay sharded"}
 
 
 class ClockSampler(threading.Thread):
@@ -110,41 +130,42 @@ def _ref_worker(args):
     return float(np.nansum(out))
 
 
-def _oracle_transform(kind, xs):
-    import oracle
-    if kind == "identity":
-        return [xs[0]]
-    if kind == "poly":
-        return [(xs[0].astype(np.float64) - 273.15) ** p for p in (1, 2, 3, 4)]
-    return [oracle.snyder_edd(xs[0], xs[1], e) for e in (283.15, 303.15)]
+class CpuReference:
+    """The oracle on `days` days of the workload, time-sharded over `procs` forked workers.  The pool is
+    created ONCE, outside the timed passes (the workers inherit the input by fork)."""
 
+    def __init__(self, workload, days, procs):
+        import multiprocessing as mp
+        from climate_toolbox_b200 import synthetic
+        deg, R, T, aggwt, kind, n_in, n_out, _ = WORKLOADS[workload]
+        if kind != "identity":
+            raise SystemExit("reference arm runs the headline identity workloads (config1/config2)")
+        lat, lon = synthetic.grid_labels(deg)
+        df = synthetic.weights_table(deg, R)
+        rng = np.random.default_rng(7)
+        x = np.empty((days, len(lat), len(lon)), dtype=np.float32)
+        for a in range(0, days, 64):                 # in slabs: the f64 temporaries of a 6 GB draw would not fit
+            b = min(days, a + 64)
+            x[a:b] = 288.0 + 10.0 * rng.standard_normal((b - a, len(lat), len(lon)), dtype=np.float32)
+        _REF.update(x=x, lat=lat, lon=lon, df=df, aggwt=aggwt)
+        self.R, self.days, self.procs = R, days, procs
+        per = max(1, -(-days // procs))
+        self.chunks = [(a, min(days, a + per)) for a in range(0, days, per)]
+        self.pool = mp.get_context("fork").Pool(procs) if procs > 1 else None
 
-def cpu_sample(workload, days, procs):
-    """Time the oracle on `days` days of the workload with `procs` forked workers."""
-    import multiprocessing as mp
-    from climate_toolbox_b200 import synthetic
-    deg, R, T, aggwt, kind, n_in, n_out, _ = WORKLOADS[workload]
-    lat, lon = synthetic.grid_labels(deg)
-    df = synthetic.weights_table(deg, R)
-    rng = np.random.default_rng(7)
-    x = (288.0 + 10.0 * rng.standard_normal((days, len(lat), len(lon)), dtype=np.float32))
-    _REF.update(x=x, lat=lat, lon=lon, df=df, aggwt=aggwt)
-    if kind != "identity":
-        raise SystemExit("reference arm runs the headline identity workloads (config1/config2)")
-    per = max(1, days // procs)
-    chunks = [(a, min(days, a + per)) for a in range(0, days, per)]
-
-    def one_pass():
+    def one_pass(self):
         t = time.perf_counter()
-        if procs == 1:
-            for c in chunks:
+        if self.pool is None:
+            for c in self.chunks:
                 _ref_worker(c)
         else:
-            with mp.get_context("fork").Pool(procs) as pool:
-                pool.map(_ref_worker, chunks)
+            self.pool.map(_ref_worker, self.chunks)
         return time.perf_counter() - t
 
-    return one_pass, R, days
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
 
 
 def run_reference(args):
@@ -154,22 +175,36 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
     deg, R, T, aggwt, kind, n_in, n_out, desc = WORKLOADS[args.workload]
-    days = procs * (8 if deg < 1 else 64)
-    one_pass, R, days = cpu_sample(args.workload, days, procs)
-    for _ in range(args.warmup):
-        one_pass()
-    ts = [one_pass() for _ in range(args.steps)]
+    days = args.days or T
+    # the whole step of the workload when the host has the memory for it (input + the workers' f64
+    # temporaries), else the largest sample that fits
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    ncell = int(round(180 / deg)) * int(round(360 / deg))
+    while days > 64 and days * ncell * 4 * 1.6 > 0.6 * avail:
+        days //= 2
+    ref = CpuReference(args.workload, days, procs)
+    try:
+        for _ in range(args.warmup):
+            ref.one_pass()
+        ts = [ref.one_pass() for _ in range(args.steps)]
+    finally:
+        ref.close()
     sec = float(np.mean(ts))
     v = R * days / sec
-    sample = "{} days of the workload per step ({} forked workers x {} days, time-sharded)".format(
-        days, procs, max(1, days // procs))
+    sample = "{} of the {} days of the workload per step ({} forked workers x {} days, time-sharded; pool created " \
+             "outside the timed passes)".format(days, T, procs, -(-days // procs))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "region-days/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": desc, "impl_note": "restated reference (oracle/oracle.py, numpy/pandas): "
-                   "xarray is not installable in this image, so the unmodified reference cannot run"},
+        "config": config_dict(args.workload, T, 1),
+        "impl_note": "restated reference (oracle/oracle.py, numpy/pandas): xarray is not installable in this "
+                     "image, so the unmodified reference cannot run",
         "cpu_baseline": {"value": v, "unit": "region-days/s", "cores": procs, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "region-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -181,133 +216,208 @@ def run_reference(args):
 # --------------------------------------------------------------------------- #
 # our arm
 # --------------------------------------------------------------------------- #
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import __graft_entry__ as G
+        G.build()
+        from climate_toolbox_b200 import _engine as E
+        from climate_toolbox_b200 import _native as N
+        from climate_toolbox_b200 import synthetic
+        self.torch, self.dist, self.E, self.N, self.syn = torch, dist, E, N, synthetic
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus {} needs torchrun with {} ranks".format(args.gpus, args.gpus))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:   # ranks share the host cores for the e2e packing
+            os.environ.setdefault("CTB_PACK_THREADS", str(max(1, (3 * (os.cpu_count() or 1)) // (4 * self.world))))
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peak, self.peak_src = _peaks()
+        self._tables = {}
 
-    import __graft_entry__ as G
-    G.build()
-    from climate_toolbox_b200 import Dataset, DataArray, synthetic
-    from climate_toolbox_b200 import _engine as E
-    from climate_toolbox_b200 import _native as N
+    # ---- helpers ---------------------------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def table(self, deg, R):
+        if (deg, R) not in self._tables:
+            self._tables[(deg, R)] = self.syn.weights_table(deg, R)
+        return self._tables[(deg, R)]
+
+    def inputs(self, workload, T, seed_off=0, variant=None):
+        """Device-resident synthetic inputs of the workload ([T, ncell] f32 views)."""
+        torch = self.torch
+        deg, R, _, aggwt, kind, n_in, n_out, _ = WORKLOADS[workload]
+        lat, lon = self.syn.grid_labels(deg)
+        g = torch.Generator(device=self.dev).manual_seed(7 + self.rank + seed_off)
+        shape = (T, len(lat) * len(lon))
+        tas = 288.0 + 10.0 * torch.randn(shape, generator=g, device=self.dev, dtype=torch.float32)
+        if n_in == 2:
+            lo = tas - (3.0 * torch.randn(shape, generator=g, device=self.dev, dtype=torch.float32)).abs()
+            hi = tas + (3.0 * torch.randn(shape, generator=g, device=self.dev, dtype=torch.float32)).abs()
+            return [lo, hi]
+        if variant in ("bcsd_like", "nan2pct"):
+            df = self.table(deg, R)
+            ii = np.searchsorted(lat, df["lat"].values)
+            jj = np.searchsorted(lon, df["lon"].values)
+            land = np.zeros(len(lat) * len(lon), dtype=bool)
+            land[ii * len(lon) + jj] = True
+            if variant == "bcsd_like":      # NaN over every gridcell no weights row references (ocean)
+                tas[:, torch.from_numpy(~land).to(self.dev)] = float("nan")
+            else:                           # 2 % of the referenced gridcells are NaN on every day
+                cells = np.flatnonzero(land)
+                pick = np.random.default_rng(3).choice(cells, size=len(cells) // 50, replace=False)
+                tas[:, torch.from_numpy(pick).to(self.dev)] = float("nan")
+        return [tas]
+
+    def timed(self, fn, steps, warmup):
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            fn()
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = self.E.launch_count()
+        self.barrier()
+        e0.record()
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        e1.record()
+        self.barrier()
+        launches = self.E.launch_count() - n0
+        total_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        return total_ms / steps, kern_ms, launches
+
+    def roofline(self, workload, plan, T, kern_ms, traffic=None):
+        deg, R, _, aggwt, kind, n_in, n_out, _ = WORKLOADS[workload]
+        balg = plan.algorithmic_bytes(T, n_in, 4, n_out)
+        achieved = balg / (kern_ms * 1e-3) / 1e9
+        hbm = {"bound": "hbm", "achieved": achieved, "peak": self.peak, "unit": "GB/s",
+               "frac": achieved / self.peak, "traffic": traffic,
+               "traffic_ratio": (traffic / balg) if traffic else None, "peak_source": self.peak_src,
+               "kernel": KERNEL[kind], "algorithmic_bytes_per_launch": balg,
+               "bytes_per_region_day": balg / (plan.R * T), "launch_ms": kern_ms,
+               "frac_of_8TBs_nominal": achieved / 8000.0}
+        if kind != "edd":
+            return hbm
+        # Snyder: max(HBM time, fp64 time) bounds the kernel (SURVEY 7.3-5 / 8d); the fp64 side is larger
+        clocks_hz = 1.965e9
+        peak_ops = FP64_LANES_PER_SM_CLK * 148 * clocks_hz
+        ops = SNYDER_FP64_OPS_PER_ENTRY_DAY * plan.info["nnz"] * T
+        ach = ops / (kern_ms * 1e-3)
+        return {"bound": "fp64", "achieved": ach / 1e12, "peak": peak_ops / 1e12, "unit": "Tinstr/s (fp64 pipe, lane-ops)",
+                "frac": ach / peak_ops, "traffic": traffic, "kernel": KERNEL[kind], "launch_ms": kern_ms,
+                "peak_source": "nominal: 64 fp64 lanes/SM/clk x 148 SMs x 1.965 GHz (no measured fp64 figure in MEASURED_PEAKS.json)",
+                "fp64_ops_per_entry_day": SNYDER_FP64_OPS_PER_ENTRY_DAY, "entry_days": plan.info["nnz"] * T,
+                "hbm": hbm}
+
+    # ---- one workload, device-resident ------------------------------------------------
+    def device_run(self, workload, steps, warmup, T=None, variant=None, groups_period=None):
+        torch, E, N = self.torch, self.E, self.N
+        deg, R, T0, aggwt, kind, n_in, n_out, desc = WORKLOADS[workload]
+        T = T or T0
+        lat, lon = self.syn.grid_labels(deg)
+        df = self.table(deg, R)
+        xs = self.inputs(workload, T, variant=variant)
+        ncell = len(lat) * len(lon)
+        t_plan = time.perf_counter()
+        plan = E.get_plan(E.GridSpec(lat, lon), df, aggwt, "hierid", stage_bytes=4 * n_in, device=self.dev)
+        torch.cuda.synchronize()
+        plan_ms = (time.perf_counter() - t_plan) * 1e3
+        groups = None
+        n_cols = T
+        if groups_period:
+            groups = E.get_time_groups(np.arange(T) // groups_period, self.dev)
+            n_cols = groups.n_groups
+        out = torch.empty((n_out, plan.R, n_cols), dtype=torch.float64, device=self.dev)
+        ws = E._workspace(plan, T, n_out, N.LAYOUT_TIME_MAJOR, N.VARIANT_AUTO, groups, None)
+        streaming = workload == "config5"
+        years = YEARS_PER_STEP if streaming else 1
+        params = PARAMS[kind]
+        if streaming:
+            pool = [xs[0]] + [self.inputs(workload, T, seed_off=100 * (k + 1))[0] for k in range(POOL - 1)]
+            chk = torch.zeros((), dtype=torch.float64, device=self.dev)
+
+        def step():
+            if streaming:
+                for y in range(YEARS_PER_STEP):
+                    E.aggregate_device(plan, pool[y % POOL], None, N.LAYOUT_TIME_MAJOR, ncell, None, T, kind,
+                                       params, n_out, out=out, workspace=ws)
+                    chk.add_(out.sum())
+                return
+            E.aggregate_device(plan, xs[0], xs[1] if n_in == 2 else None, N.LAYOUT_TIME_MAJOR, ncell,
+                               None, T, kind, params, n_out, out=out, workspace=ws, groups=groups)
+
+        ms_step, kern_ms, launches = self.timed(step, steps, warmup)
+        if streaming:
+            kern_ms = ms_step / years
+        res = {"plan": plan, "xs": xs, "out": out, "T": T, "ms_per_step": ms_step, "kern_ms": kern_ms,
+               "launches": launches, "years": years, "plan_ms": plan_ms,
+               "value": self.world * plan.R * T * years / (ms_step * 1e-3),
+               "checksum": float(torch.nansum(out).item())}
+        return res
+
+    def summary(self, workload, r, traffic=None, extra=None):
+        """Compact entry of the `also` block."""
+        info = r["plan"].info
+        d = {"workload": WORKLOADS[workload][7], "T": r["T"], "ms_per_launch": r["kern_ms"],
+             "region_days_per_s": r["value"], "roofline": self.roofline(workload, r["plan"], r["T"], r["kern_ms"], traffic),
+             "bundles": info["n_bundles"], "gpu_launches": r["launches"], "checksum": r["checksum"]}
+        d["roofline"].pop("peak_source", None)
+        if extra:
+            d.update(extra)
+        return d
+
+
+def run_ours(args):
+    B = Bench(args)
+    torch, dist, E, N = B.torch, B.dist, B.E, B.N
+    from climate_toolbox_b200 import DataArray, Dataset
     from climate_toolbox_b200.aggregations.aggregations import weighted_aggregate_grid_to_regions
     from climate_toolbox_b200.transformations.transformations import snyder_edd
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus {} needs torchrun with {} ranks".format(args.gpus, args.gpus))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:   # ranks share the host cores for the e2e packing
-        os.environ.setdefault("CTB_PACK_THREADS", str(max(1, (3 * (os.cpu_count() or 1)) // (4 * world))))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    rank, world, dev = B.rank, B.world, B.dev
     deg, R, T, aggwt, kind, n_in, n_out, desc = WORKLOADS[args.workload]
     if args.days:
         T = args.days
-    lat, lon = synthetic.grid_labels(deg)
-    df = synthetic.weights_table(deg, R)
-    g = torch.Generator(device=dev).manual_seed(7 + rank)
-    shape = (T, len(lat), len(lon))
-    tas = 288.0 + 10.0 * torch.randn(shape, generator=g, device=dev, dtype=torch.float32)
-    xs = [tas]
-    if n_in == 2:
-        lo = tas - (3.0 * torch.randn(shape, generator=g, device=dev, dtype=torch.float32)).abs()
-        hi = tas + (3.0 * torch.randn(shape, generator=g, device=dev, dtype=torch.float32)).abs()
-        xs = [lo, hi]
-        del tas
-    params = {"identity": (), "poly": (273.15, 1, 2, 3, 4), "edd": (283.15, 303.15)}[kind]
-
-    grid = E.GridSpec(lat, lon)
-    t_plan = time.perf_counter()
-    plan = E.get_plan(grid, df, aggwt, "hierid", stage_bytes=4 * n_in, device=dev,
-                      smem_budget=args.smem_budget)
-    torch.cuda.synchronize()
-    plan_ms = (time.perf_counter() - t_plan) * 1e3
-    info = plan.info
+    lat, lon = B.syn.grid_labels(deg)
+    df = B.table(deg, R)
     ncell = len(lat) * len(lon)
-    x2 = [x.view(T, ncell) for x in xs]
-    out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
-    ws_bytes = N.lib().ctb_aggregate_workspace_bytes(plan._h, T, n_out)
-    ws = torch.empty(max(1, ws_bytes // 8), dtype=torch.float64, device=dev)
-
-    streaming = args.workload == "config5"
-    years = YEARS_PER_STEP if streaming else 1
-    if streaming:   # more resident model-years (the first is `tas`), outputs checksummed and discarded
-        pool = [x2[0]] + [(288.0 + 10.0 * torch.randn(shape, generator=g, device=dev, dtype=torch.float32)
-                           ).view(T, ncell) for _ in range(POOL - 1)]
-        chk = torch.zeros((), dtype=torch.float64, device=dev)
-
-    def step():
-        if streaming:
-            for y in range(YEARS_PER_STEP):
-                E.aggregate_device(plan, pool[y % POOL], None, N.LAYOUT_TIME_MAJOR, ncell, None, T, kind,
-                                   params, n_out, args.variant, out=out, workspace=ws)
-                chk.add_(out.sum())
-            return
-        E.aggregate_device(plan, x2[0], x2[1] if n_in == 2 else None, N.LAYOUT_TIME_MAJOR, ncell,
-                           None, T, kind, params, n_out, args.variant, out=out, workspace=ws)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    n0 = E.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for a, b in evs:
-        a.record()
-        step()
-        b.record()
-    e1.record()
-    barrier()
-    launches = E.launch_count() - n0
-    total_ms = e0.elapsed_time(e1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    clocks = sampler.result()
-    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
-    ms_per_step = total_ms / args.steps
-    value = world * plan.R * T * years / (ms_per_step * 1e-3)
-    checksum = float(torch.nansum(out).item())
-
-    # ---- roofline of the dominant kernel (the fused staged kernel = the whole step) ----
-    balg = plan.algorithmic_bytes(T, n_in, 4, n_out)   # per launch (config5: one model-year)
-    if streaming:   # per launch, including the checksum reductions between launches
-        kern_ms = total_ms / args.steps / years
-    peak, peak_src = _peaks()
-    achieved = balg / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic_all = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "agg_fused_kernel", "algorithmic_bytes_per_launch": balg,
-                "bytes_per_region_day": balg / (plan.R * T), "launch_ms": kern_ms,
-                "frac_of_8TBs_nominal": achieved / 8000.0}
+        traffic_all = json.load(open(tp))
 
-    # ---- end to end through the public API with HOST (pinned) buffers ----
+    sampler = ClockSampler(B.local)
+    sampler.start()
+    head = B.device_run(args.workload, args.steps, args.warmup, T=T)
+    clocks = sampler.result()
+    plan, xs, out = head["plan"], head["xs"], head["out"]
+    info = plan.info
+    roofline = B.roofline(args.workload, plan, T, head["kern_ms"], traffic_all.get(args.workload))
+    streaming = args.workload == "config5"
+
+    # ---- end to end through the public API with HOST buffers ----
     e2e = None
     if not args.no_e2e and not streaming:
         # every rank pins its own host copy of the batch: keep the node's total under 40 % of the
         # free host memory (8 ranks x 6 GB would not fit a small host) by shortening the e2e batch
-        T_full = T
+        Te = T
         try:
             import psutil
             avail = psutil.virtual_memory().available
@@ -315,129 +425,181 @@ def run_ours(args):
             avail = 32 << 30
         need = world * len(xs) * T * ncell * 4
         if need > 0.4 * avail:
-            T = max(64, int(T * 0.4 * avail / need) // 32 * 32)
+            Te = max(64, int(T * 0.4 * avail / need) // 32 * 32)
         if world > 1:
-            tmin = torch.tensor([T], device=dev, dtype=torch.int64)
+            tmin = torch.tensor([Te], device=dev, dtype=torch.int64)
             dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-            T = int(tmin.item())
-        shape = (T, len(lat), len(lon))
+            Te = int(tmin.item())
+        shape = (Te, len(lat), len(lon))
         host = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in xs]
         for h, x in zip(host, xs):
-            h.copy_(x[:T])
+            h.copy_(x[:Te].view(shape))
         torch.cuda.synchronize()
-        coords = {"time": np.arange(T), "lat": lat, "lon": lon}
+        coords = {"time": np.arange(Te), "lat": lat, "lon": lon}
         dims = ("time", "lat", "lon")
-        if kind == "identity":
-            ds = Dataset({"tas": (dims, host[0].numpy())}, coords=coords)
-            names = "tas"
-        elif kind == "poly":
-            from climate_toolbox_b200._xr import Deferred, Variable
-            src = Variable(dims, host[0].numpy())
-            ds = Dataset(coords=coords)
-            names = ["p1", "p2", "p3", "p4"]
-            for p, nme in zip((1, 2, 3, 4), names):
-                ds._vars[nme] = Variable(dims, None, None, None, Deferred("poly", (273.15, float(p)), (src,)))
-        else:
-            tn = DataArray(host[0].numpy(), dims=dims, coords=coords, attrs={"units": "K"})
-            tx = DataArray(host[1].numpy(), dims=dims, coords=coords, attrs={"units": "K"})
+
+        def make_ds(arrays):
+            if kind == "identity":
+                return Dataset({"tas": (dims, arrays[0])}, coords=coords), "tas"
+            if kind == "poly":
+                from climate_toolbox_b200._xr import Deferred, Variable
+                src = Variable(dims, arrays[0])
+                ds = Dataset(coords=coords)
+                names = ["p1", "p2", "p3", "p4"]
+                for p, nme in zip((1, 2, 3, 4), names):
+                    ds._vars[nme] = Variable(dims, None, None, None, Deferred("poly", (273.15, float(p)), (src,)))
+                return ds, names
+            tn = DataArray(arrays[0], dims=dims, coords=coords, attrs={"units": "K"})
+            tx = DataArray(arrays[1], dims=dims, coords=coords, attrs={"units": "K"})
             ds = Dataset(coords=coords)
             ds["edd10"] = snyder_edd(tn, tx, 283.15, check=False)
             ds["edd30"] = snyder_edd(tn, tx, 303.15, check=False)
-            names = ["edd10", "edd30"]
+            return ds, ["edd10", "edd30"]
 
-        def e2e_step():
-            r = weighted_aggregate_grid_to_regions(ds, names, aggwt, "hierid", weights=df,
-                                                   smem_budget=args.smem_budget)
-            return r
+        def measure(ds, names, steps, min_warm=3, warm_s=2.5, **opts):
+            # warm-up: pinned staging/result blocks come from pools, and the host needs a moment after a
+            # multi-GB pinned source was allocated and filled -- at least 3 calls and 2.5 s
+            t_w, n_w = time.perf_counter(), 0
+            while n_w < min_warm or (time.perf_counter() - t_w < warm_s and n_w < 30):
+                r = weighted_aggregate_grid_to_regions(ds, names, aggwt, "hierid", weights=df, **opts)
+                n_w += 1
+            B.barrier()
+            E.TRANSFER_BYTES.update(h2d=0, d2h=0)
+            t0 = time.perf_counter()
+            step_ms = []
+            for _ in range(steps):
+                ts = time.perf_counter()
+                r = weighted_aggregate_grid_to_regions(ds, names, aggwt, "hierid", weights=df, **opts)
+                step_ms.append(round((time.perf_counter() - ts) * 1e3, 1))      # returns host arrays: synchronous
+            torch.cuda.synchronize()
+            B.barrier()
+            dt = B.max_over_ranks((time.perf_counter() - t0) / steps)
+            first = names if isinstance(names, str) else names[0]
+            return {"value": world * plan.R * Te / dt, "ms_per_step": dt * 1e3, "step_ms": step_ms,
+                    "h2d_bytes_per_step": int(E.TRANSFER_BYTES["h2d"] // steps),
+                    "d2h_bytes_per_step": int(E.TRANSFER_BYTES["d2h"] // steps), "warmup_calls": n_w,
+                    "checksum": float(np.nansum(r[first].values))}
 
-        e2e_steps = max(2, min(args.steps, 10))   # ~0.1 s each; the shared host's spikes average out a little
-        # warm-up: pinned staging/result blocks come from pools, and the host needs a moment after the
-        # 6 GB pinned source was allocated and filled (the first second of calls runs 3-5x slower) --
-        # at least 3 calls and 2.5 s, whichever is longer
-        t_w, n_w = time.perf_counter(), 0
-        while n_w < 3 or (time.perf_counter() - t_w < 2.5 and n_w < 30):
-            r = e2e_step()
-            n_w += 1
-        barrier()
-        E.TRANSFER_BYTES.update(h2d=0, d2h=0)
-        t0 = time.perf_counter()
-        step_ms = []
-        for _ in range(e2e_steps):
-            ts = time.perf_counter()
-            r = e2e_step()          # returns host arrays: the call is synchronous
-            step_ms.append(round((time.perf_counter() - ts) * 1e3, 1))
-        torch.cuda.synchronize()
-        barrier()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        h2d_step = E.TRANSFER_BYTES["h2d"] // e2e_steps
-        d2h_step = E.TRANSFER_BYTES["d2h"] // e2e_steps
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        first = names if isinstance(names, str) else names[0]
-        e2e_check = float(np.nansum(r[first].values))
-        e2e = {"value": world * plan.R * T / dt, "unit": "region-days/s",
-               "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+        e2e_steps = max(2, min(args.steps, 10))
+        ds, names = make_ds([h.numpy() for h in host])
+        m = measure(ds, names, e2e_steps)
+        e2e = {"value": m["value"], "unit": "region-days/s", "h2d_bytes_per_step": m["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": m["d2h_bytes_per_step"],
                "host_input_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
-               "ms_per_step": dt * 1e3, "days_per_step": T, "step_ms": step_ms, "warmup_calls": n_w,
+               "ms_per_step": m["ms_per_step"], "days_per_step": Te, "step_ms": m["step_ms"],
+               "warmup_calls": m["warmup_calls"], "steps": e2e_steps,
                "pinned_result_blocks_allocated": int(sum(E._RESULT_OUT.values())),
-               "steps": e2e_steps, "api": "weighted_aggregate_grid_to_regions(ds[numpy over pinned host "
-               "memory], ...) -> Dataset[numpy]: host packing of the referenced gridcells + pinned chunked "
-               "H2D + fused kernel + pinned D2H",
-               "checksum": e2e_check}
-        del host
-        T = T_full
+               "api": "weighted_aggregate_grid_to_regions(ds[numpy over pinned host memory], ...) -> Dataset[numpy]: "
+                      "host packing of the referenced gridcells + pinned chunked H2D + fused kernel + pinned D2H",
+               "checksum": m["checksum"]}
+        if kind == "identity":
+            # the step after the path fused in (annual sums): the result block shrinks 365x
+            my = measure(ds, names, max(2, e2e_steps // 2), min_warm=2, warm_s=0.5, time_groups=365)
+            e2e["annual_sums"] = {k: my[k] for k in ("value", "ms_per_step", "step_ms", "h2d_bytes_per_step",
+                                                     "d2h_bytes_per_step")}
+        if world == 1 and kind == "identity" and not args.no_pageable:
+            # a load_bcsd user holds PAGEABLE memory: same call on a plain numpy copy of a 365-day block
+            Tp = min(Te, 365)
+            pag = [np.array(h.numpy()[:Tp]) for h in host]
+            coords_p = dict(coords, time=np.arange(Tp))
+            dsp = Dataset({"tas": (dims, pag[0])}, coords=coords_p)
+            keep_Te, Te = Te, Tp
+            mp_ = measure(dsp, "tas", max(2, e2e_steps // 2), min_warm=2, warm_s=0.5)
+            Te = keep_Te
+            e2e["pageable_source"] = {"days_per_step": Tp, **{k: mp_[k] for k in ("value", "ms_per_step", "step_ms",
+                                                                                  "h2d_bytes_per_step")}}
+            del pag, dsp
+        del host, ds
 
-    # ---- optional: the final gather of region x time outputs (north_star) ----
-    gather = None
-    if world > 1:
-        from climate_toolbox_b200.parallel import all_gather_time  # noqa: F401
-        bufs = [torch.empty_like(out) for _ in range(world)]
-        dist.all_gather(bufs, out)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.all_gather(bufs, out)
-        g1.record()
-        barrier()
-        gather = {"ms": g0.elapsed_time(g1), "bytes_per_rank": int(out.numel() * 8),
-                  "note": "NCCL all_gather of every rank's [n_out][R][T] f64 block; not in `value`"}
+    # ---- strong scaling: ONE batch sharded along time, compute + final gather (north_star) ----
+    strong = None
+    if world > 1 and not streaming and kind == "identity":
+        from climate_toolbox_b200.parallel import aggregate_shard_overlapped, shard_sizes
+        x = xs[0]
+        full = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
+
+        def run(gather, pieces):
+            def f():
+                aggregate_shard_overlapped(plan, x, None, ncell, T, kind, PARAMS[kind], n_out, pieces=pieces,
+                                           gather=gather, out=full if gather else None)
+            return f
+
+        s_steps = max(3, min(args.steps, 10))
+        comp_ms, _, _ = B.timed(run(False, 1), s_steps, 3)
+        seq_ms, _, _ = B.timed(run(True, 1), s_steps, 3)
+        ovl_ms, _, _ = B.timed(run(True, 4), s_steps, 3)
+        sizes = shard_sizes(T, world)
+        strong = {"what": "one {}-day batch sharded along time over {} ranks (plan replicated); final NCCL all_gather of "
+                          "the region x time blocks into [R][T] on every rank".format(T, world),
+                  "days_per_rank": sizes, "compute_ms": comp_ms, "compute_plus_gather_ms": seq_ms,
+                  "overlapped_ms": ovl_ms, "gather_ms": seq_ms - comp_ms,
+                  "bytes_received_per_rank": int(8 * n_out * plan.R * (T - min(sizes))),
+                  "value": plan.R * T / (ovl_ms * 1e-3), "value_compute_only": plan.R * T / (comp_ms * 1e-3),
+                  "unit": "region-days/s", "scaling": "strong",
+                  "limiter": "the fp64 all_gather: every rank receives (N-1)/N of the 285 MB output over NVLink"}
+        del full
+
+    # ---- the other configs and input variants (N = 1: device-timed, 10 steps each) ----
+    also = None
+    if world == 1 and not args.no_also and args.workload == "config2" and not args.days:
+        also = {}
+        del xs
+        head["xs"] = None
+        torch.cuda.empty_cache()
+        st = max(5, min(args.steps, 10))
+        for name, wl, kw in (("config2_bcsd_like", "config2", {"variant": "bcsd_like"}),
+                             ("config2_nan_2pct_of_land", "config2", {"variant": "nan2pct"}),
+                             ("config2_annual_sums", "config2", {"groups_period": 365}),
+                             ("config3", "config3", {}), ("config4", "config4", {}),
+                             ("config1", "config1", {}), ("config5", "config5", {})):
+            r = B.device_run(wl, st, 3, **kw)
+            extra = None
+            if wl == "config5":
+                extra = {"model_years_per_step": r["years"], "pool_buffers": POOL,
+                         "full_job_model_years": ENSEMBLE_YEARS,
+                         "full_job_seconds_extrapolated": ENSEMBLE_YEARS / r["years"] * r["ms_per_step"] * 1e-3}
+            if name == "config2_annual_sums":
+                extra = {"note": "fused time reduction: output [R][4 years] instead of [R][1460 days]"}
+            also[name] = B.summary(wl, r, traffic_all.get(name), extra)
+            del r
+            torch.cuda.empty_cache()
+
+    # ---- ensemble (config 5) at N ranks: model-years dealt round-robin, outputs stay with their owner ----
+    ensemble = None
+    if streaming:
+        ensemble = {"model_years_per_step_per_rank": head["years"], "pool_buffers": POOL,
+                    "full_job_model_years": ENSEMBLE_YEARS, "ranks": world,
+                    "full_job_seconds_extrapolated": ENSEMBLE_YEARS / (head["years"] * world) * head["ms_per_step"] * 1e-3,
+                    "note": "outputs are summed into a checksum and discarded; e2e is not measured for this "
+                            "workload (6 TB of input do not exist on the host)"}
 
     # ---- CPU baseline: the oracle on a bounded sample, rank 0, N = 1 only ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and kind == "identity":
-        days = 365 if deg < 1 else 365
-        one_pass, R_, days = cpu_sample(args.workload, days, 1)
-        sec = one_pass()
+        days = 365
+        ref = CpuReference(args.workload, days, 1)
+        sec = ref.one_pass()
         cpu = {"value": plan.R * days / sec, "unit": "region-days/s", "cores": 1, "kind": "port",
                "sample": "{} days of the workload, single process (the reference is single-threaded "
                          "eager numpy), {:.1f} s; host has {} cores".format(days, sec, os.cpu_count())}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "region-days/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "metric": METRIC, "value": head["value"], "unit": "region-days/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "T": T, "grid": [len(lat), len(lon)], "regions": plan.R,
-                       "input_dtype": "f32", "accumulate": "f64", "n_in": n_in, "n_out": n_out,
-                       "l2": "inputs larger than L2 ({:.2f} GB per step)".format(n_in * T * ncell * 4 / 1e9),
-                       "U": info["n_cells_distinct"], "nnz": info["nnz"], "bundles": info["n_bundles"],
-                       "staged_pieces": info["n_pieces"], "distinct_pieces": info["n_pieces_distinct"],
-                       "plan_build_ms": plan_ms, "variant": args.variant,
-                       "per_rank": "own batch, plan replicated, outputs stay sharded"},
-            **({"ensemble": {"model_years_per_step": years, "pool_buffers": POOL,
-                             "full_job_model_years": ENSEMBLE_YEARS,
-                             "full_job_seconds_extrapolated": ENSEMBLE_YEARS / (years * world) * ms_per_step * 1e-3,
-                             "note": "outputs are summed into a checksum and discarded; e2e is not measured "
-                                     "for this workload (6 TB of input do not exist on the host)"}}
-               if streaming else {}),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "checksum": checksum,
+            "config": config_dict(args.workload, T, world),
+            "plan": {"U": info["n_cells_distinct"], "nnz": info["nnz"], "bundles": info["n_bundles"],
+                     "staged_pieces": info["n_pieces"], "distinct_pieces": info["n_pieces_distinct"],
+                     "quads": info["n_quads"], "quads_with_bank_conflict": info["n_quads_conflict"],
+                     "plan_build_ms": head["plan_ms"]},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(head["launches"]),
+            "clocks": clocks, "checksum": head["checksum"],
         }
-        if gather:
-            line["gather"] = gather
+        for k, v in (("strong", strong), ("also", also), ("ensemble", ensemble)):
+            if v is not None:
+                line[k] = v
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -451,10 +613,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--days", type=int, default=0, help="override T (debug)")
-    ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--smem-budget", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the device-timed lines of the other configs")
+    ap.add_argument("--no-pageable", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

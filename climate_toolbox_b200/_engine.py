@@ -392,8 +392,17 @@ class _PinnedOwner:
                                     "data": (block.data_ptr(), False), "version": 3}
 
 
+RESULT_POOL_CAP_BYTES = int(os.environ.get("CTB_RESULT_POOL_BYTES", str(2 << 30)))
+
+
 def _release_result(block):
-    _RESULT_POOL.setdefault(block.numel(), []).append(block)
+    """A result's last view is gone: keep its pinned block for the next result of that size, unless the
+    idle blocks already hold RESULT_POOL_CAP_BYTES of page-locked memory (then it is freed)."""
+    idle = sum(b.numel() for blocks in _RESULT_POOL.values() for b in blocks)
+    if idle + block.numel() <= RESULT_POOL_CAP_BYTES:
+        _RESULT_POOL.setdefault(block.numel(), []).append(block)
+    else:
+        _RESULT_OUT[block.numel()] = max(0, _RESULT_OUT.get(block.numel(), 1) - 1)
 
 
 def pinned_result_like(t):
@@ -444,19 +453,78 @@ def pack_threads():
     return max(1, (3 * ncpu) // 4)
 
 
+def _aggregate_pull(plan, xs, stride, tix, T, kind, params, n_out, variant, groups, out, host_out=None,
+                    chunk_bytes=4 << 30):
+    """Pinned host arrays + compact plan: the GPU packs for itself (``ctb_pull_pack`` reads the
+    referenced pieces over PCIe into a packed device buffer), then the kernel aggregates the packed
+    planes.  No host core touches the data; pulls and kernels queue on one stream.  With ``host_out``
+    (a pinned [n_out, R, T] tensor) the result goes back in time chunks on a second stream while the
+    next chunk is pulled (PCIe is full duplex); the caller then only has to synchronise."""
+    dev = plan.device
+    itemsize = xs[0].dtype.itemsize
+    width = plan.info["n_packed_cells"]
+    tdt = torch.float32 if itemsize == 4 else torch.float64
+    days = max(32, int(chunk_bytes // max(width * itemsize * len(xs), 1)) // 32 * 32)
+    if host_out is not None and groups is None:
+        days = min(days, max(32, (-(-T // 4) + 31) // 32 * 32))      # about four chunks: the last D2H is exposed
+    tix_d = plan.time_index_device(tix)
+    ws = _workspace(plan, min(days, T), n_out, N.LAYOUT_TIME_MAJOR, variant, groups, None)
+    starts = list(range(0, T, days))
+    main = torch.cuda.current_stream(dev)
+    back = torch.cuda.Stream(dev) if host_out is not None and groups is None else None
+    for t0 in starts:
+        n = min(T, t0 + days) - t0
+        bufs = []
+        for x in xs:
+            b = torch.empty((n, width), dtype=tdt, device=dev)
+            N.check(N.lib().ctb_pull_pack(
+                plan._h, C.c_void_p(x.ctypes.data), _NP2CTB[x.dtype], int(stride),
+                C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(t0), int(n),
+                C.c_void_p(b.data_ptr()), _stream_ptr(dev)))
+            bufs.append(b)
+        TRANSFER_BYTES["h2d"] += len(xs) * n * plan.info["n_pieces_distinct"] * 4 * itemsize
+        if groups is None:
+            aggregate_device(plan, bufs[0], bufs[1] if len(bufs) > 1 else None, N.LAYOUT_TIME_MAJOR, width, None,
+                             n, kind, params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
+            if back is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                back.wait_event(ev)
+                N.check(N.lib().ctb_copy_rows_to_host(
+                    C.c_void_p(host_out.data_ptr() + 8 * t0), 8 * T, C.c_void_p(out.data_ptr() + 8 * t0), 8 * T,
+                    8 * n, n_out * plan.R, C.c_void_p(back.cuda_stream)))
+                TRANSFER_BYTES["d2h"] += 8 * n * n_out * plan.R
+        else:
+            aggregate_device(plan, bufs[0], bufs[1] if len(bufs) > 1 else None, N.LAYOUT_TIME_MAJOR, width, None,
+                             n, kind, params, n_out, variant, out=out, workspace=ws, groups=groups, t_begin=t0,
+                             flush=(t0 == starts[-1]))
+    if back is not None:
+        out.record_stream(back)
+        main.wait_stream(back)
+        return out, True
+    return out, False
+
+
 def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(), n_out=1,
-                   variant=N.VARIANT_AUTO, chunk_bytes=192 << 20, zero_copy=None, threads=0, groups=None):
+                   variant=N.VARIANT_AUTO, chunk_bytes=192 << 20, zero_copy=None, threads=0, groups=None,
+                   ingest=None, host_out=None):
     """Host (numpy) inputs -> CUDA tensor [n_out, R, T] (with ``groups``: [n_out, R, n_groups]).
 
     ``xs``: list of 1 or 2 C-contiguous numpy arrays viewed as 2-D
     (TIME_MAJOR: [t_phys, stride]; CELL_MAJOR: [ncell, stride]).
 
-    * compact plan (the default for TIME_MAJOR host inputs): time chunks are PACKED on the
+    * compact plan (the default for TIME_MAJOR host inputs), source in PINNED memory: the GPU pulls
+      the referenced gridcells over PCIe itself (``ctb_pull_pack``; ``ingest="pull"``);
+    * compact plan, pageable source (``ingest="pack"``): time chunks are PACKED on the
       host (``ctb_host_pack``, all cores) into pinned staging buffers that hold only the
       referenced gridcells, copied asynchronously and reduced while the next chunk is packed;
     * full-grid plan: time chunks are copied whole (pinned: asynchronously at PCIe speed;
       pageable: through the driver's staging), or -- opt-in, pinned arrays only -- read in
       place by the kernel (zero-copy).
+
+    ``host_out``: ``[pinned tensor [n_out, R, T], False]`` -- a path that can return the result in
+    time chunks while later chunks are still in flight fills the tensor and sets the flag (the
+    caller synchronises the stream); otherwise the flag stays False and the caller copies ``out``.
     """
     dev = plan.device
     n_cols = T if groups is None else groups.n_groups
@@ -479,6 +547,20 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
         return _launch(plan, xs[0].ctypes.data, xs[1].ctypes.data if len(xs) > 1 else 0,
                        _NP2CTB[xs[0].dtype], layout, stride, tix, T, kind, params, n_out,
                        N.VARIANT_STAGED | 0x100, out, 0, None, None, groups)
+
+    if ingest is None:
+        ingest = os.environ.get("CTB_INGEST", "auto")
+    if plan.compact and ingest in ("auto", "pull") and xs[0].dtype in _NP2CTB and \
+            (stride * xs[0].dtype.itemsize) % 16 == 0 and (plan.info["n_cells_grid"] % 4 == 0) and \
+            all(x.ctypes.data % 16 == 0 for x in xs) and _all_pinned(xs):
+        # pinned (device-accessible) source: the GPU pulls the referenced pieces itself
+        out, filled = _aggregate_pull(plan, xs, stride, tix, T, kind, params, n_out, variant, groups, out,
+                                      host_out[0] if host_out is not None else None)
+        if host_out is not None:
+            host_out[1] = filled
+        return out
+    if ingest == "pull":
+        raise ValueError("ingest='pull' needs a compact plan and 16-byte aligned inputs in pinned host memory")
 
     threads = threads or pack_threads()
     main = torch.cuda.current_stream(dev)

@@ -24,7 +24,7 @@ SYMBOLS = (
     "ctb_version", "ctb_last_error", "ctb_launch_count", "ctb_plan_build", "ctb_plan_free",
     "ctb_plan_get_info", "ctb_plan_row_cells", "ctb_plan_den", "ctb_plan_row_weights",
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
-    "ctb_host_pack", "ctb_time_groups_create", "ctb_time_groups_free", "ctb_time_groups_count",
+    "ctb_host_pack", "ctb_pull_pack", "ctb_copy_rows_to_host", "ctb_time_groups_create", "ctb_time_groups_free", "ctb_time_groups_count",
     "ctb_aggregate_grouped_workspace_bytes", "ctb_aggregate_grouped",
 )
 
@@ -88,6 +88,10 @@ def lib():
     L.ctb_transform.argtypes = [vp, vp, C.c_int, i64, C.c_int, dp, C.c_int, C.c_int, vp, vp]
     L.ctb_gather_rows.restype = C.c_int
     L.ctb_gather_rows.argtypes = [p, vp, C.c_int, C.c_int, i64, vp, i64, vp, vp]
+    L.ctb_pull_pack.restype = C.c_int
+    L.ctb_pull_pack.argtypes = [p, vp, C.c_int, i64, vp, i64, i64, vp, vp]
+    L.ctb_copy_rows_to_host.restype = C.c_int
+    L.ctb_copy_rows_to_host.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     L.ctb_time_groups_create.restype = C.c_int
     L.ctb_time_groups_create.argtypes = [ip, i64, C.c_int, C.POINTER(p)]
     L.ctb_time_groups_free.restype = None

@@ -118,7 +118,7 @@ def _coord_labels(ds, name):
     return np.asarray(ds._coords[name].values, dtype=np.float64)
 
 
-def _run_group(plan, views, kind, params, n_out, variant, groups=None):
+def _run_group(plan, views, kind, params, n_out, variant, groups=None, ingest=None, host_out=None):
     """One fused launch for `n_out` outputs sharing the same sources."""
     v0 = views[0]
     if v0.on_device:
@@ -127,7 +127,7 @@ def _run_group(plan, views, kind, params, n_out, variant, groups=None):
                                  groups=groups)
     else:
         out = E.aggregate_host(plan, [v.data2d for v in views], v0.layout, v0.stride, v0.tix, v0.T,
-                               kind, params, n_out, variant, groups=groups)
+                               kind, params, n_out, variant, groups=groups, ingest=ingest, host_out=host_out)
     return out
 
 
@@ -193,7 +193,7 @@ def _group_requests(reqs):
 
 def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant=N.VARIANT_AUTO,
                     device=None, smem_budget=0, keep_on_device=False, pack_host=True, trusted_weights=False,
-                    time_groups=None, time_dim="time"):
+                    time_groups=None, time_dim="time", ingest=None):
     lat, lon = _coord_labels(ds, "lat"), _coord_labels(ds, "lon")
     reqs = []
     for name in variables:
@@ -229,7 +229,13 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
             gid, glabels = _time_group_ids(ds, time_dim, v0.T, time_groups)
             groups = E.get_time_groups(gid, dev)
             other_shape = (groups.n_groups,)
-        out = _run_group(plan, views, g["kind"], g["params"], n_out, variant, groups)  # [n_out, R, T]
+        # host inputs, host result: the result block is handed to the engine, which may fill it in time
+        # chunks while later chunks are still in flight
+        host_fill = None
+        if not keep_on_device and not v0.on_device and groups is None and v0.T > 0 and plan.R > 0:
+            host, res_np = E.pinned_result_like(torch.empty((n_out, plan.R, v0.T), dtype=torch.float64, device="meta"))
+            host_fill = [host, False]
+        out = _run_group(plan, views, g["kind"], g["params"], n_out, variant, groups, ingest, host_fill)  # [n_out, R, T]
         # reference dim order: agglev takes the place of the first of (lat, lon)
         tmpl = ds._vars[g["names"][0]].dims
         first = min(tmpl.index("lat"), tmpl.index("lon"))
@@ -240,9 +246,13 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
             # D2H into pinned memory (57 GB/s on the round-1 box; a pageable copy runs at
             # 2 GB/s).  The block comes from a pool and returns to it when the last view of
             # the returned arrays is garbage collected.
-            host, res = E.pinned_result_like(out)
-            host.copy_(out, non_blocking=True)
-            E.TRANSFER_BYTES["d2h"] += out.numel() * out.element_size()
+            if host_fill is not None:
+                host, res = host_fill[0], res_np
+            else:
+                host, res = E.pinned_result_like(out)
+            if host_fill is None or not host_fill[1]:
+                host.copy_(out, non_blocking=True)
+                E.TRANSFER_BYTES["d2h"] += out.numel() * out.element_size()
             torch.cuda.current_stream(out.device).synchronize()
         R = plan.R
         for j, name in enumerate(g["names"]):

@@ -122,6 +122,7 @@ struct ctb_plan {
   // compact plans: physical piece of every packed piece, as runs of consecutive pieces
   struct PackRun { int32_t phys_piece, n_pieces, packed_piece; };
   std::vector<PackRun> h_pack_runs;
+  int32_t* d_pack_src = nullptr;   // compact plans: [n_packed_cells / 4] physical piece of every packed piece, -1 = padding
   int compact = 0;
   int elem_bytes = 4;   // element size the staged-cell byte offsets were built for
   int stage_bytes = 4;  // staged bytes per gridcell-day the bundles were sized for (n_in * elem_bytes)
@@ -294,10 +295,12 @@ template <int NOUT>
 __device__ __forceinline__ void ctb_emit(const AggArgs& a, int target, double rden, const double (&v)[NOUT],
                                          int lane, int t, bool valid, int tb, int tg, int tg0) {
   if (target >= 0 && a.tgroup) {
+    // columns this tile touches: most 32-day tiles lie inside one period
+    const int nk = __reduce_max_sync(0xffffffffu, tg) - tg0 + 1;
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) {
       const double val = v[j] * rden;
-      for (int k = 0; k < a.gk; ++k) {
+      for (int k = 0; k < nk; ++k) {
         double x = (tg == tg0 + k) ? val : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);

@@ -295,7 +295,7 @@ extern "C" void ctb_plan_free(ctb_plan* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->d_row_cell); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_w);
-  cudaFree(p->d_den); cudaFree(p->d_b_blob_off); cudaFree(p->d_b_desc); cudaFree(p->d_unit_tab); cudaFree(p->d_work_counter);
+  cudaFree(p->d_den); cudaFree(p->d_b_blob_off); cudaFree(p->d_b_desc); cudaFree(p->d_unit_tab); cudaFree(p->d_work_counter); cudaFree(p->d_pack_src);
   cudaFree(p->d_blob); cudaFree(p->d_split_region); cudaFree(p->d_split_slot_ptr);
   cudaSetDevice(prev);
   delete p;
@@ -502,6 +502,11 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
     }
     plan_ncell = (int64_t)cur * CTB_PIECE;
     P->ncell = plan_ncell;   // what the kernels index
+    // device copy for ctb_pull_pack: source piece of every packed piece
+    std::vector<int32_t> pack_src((size_t)cur, -1);
+    for (const auto& r : P->h_pack_runs)
+      for (int32_t k = 0; k < r.n_pieces; ++k) pack_src[(size_t)r.packed_piece + k] = r.phys_piece + k;
+    if (int rc_ = upload(&P->d_pack_src, pack_src)) return rc_;
   }
 
   // ---- staging bundles ----
@@ -790,5 +795,67 @@ extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_
   for (int i = 1; i < n_threads; ++i) pool.emplace_back(loop);
   loop();   // the calling thread packs too
   for (auto& th : pool) th.join();
+  return CTB_OK;
+}
+
+
+// ---------------------------------------------------------------- device ingest ---
+// The same packing done by the GPU: the referenced 16-byte pieces of T day planes are read straight
+// from a host array in pinned (device-accessible) memory over PCIe and written to a packed device
+// buffer dst[T][n_packed_cells].  Only the referenced gridcells cross the bus and no host core
+// touches the data -- what the ranks of a multi-GPU job need when they share the host's cores.
+// Thread = one packed piece x 4 consecutive days (4 independent 16-byte loads in flight per
+// thread); reads are contiguous along a run of referenced pieces, writes are fully coalesced.
+namespace {
+__global__ void __launch_bounds__(256) pull_pack_kernel(const uint4* __restrict__ src, int64_t stride16,
+                                                        const int32_t* __restrict__ tix, int64_t t_begin, int T,
+                                                        const int32_t* __restrict__ pack_src, int n_units,
+                                                        int halves, uint4* __restrict__ dst) {
+  const int64_t n_work = (int64_t)n_units * ((T + 3) / 4);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_work; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i % n_units);
+    const int d0 = (int)(i / n_units) * 4;
+    const int p = __ldg(pack_src + u / halves);
+    if (p < 0) continue;                       // alignment padding of the packed plane: never read
+    const int64_t so = (int64_t)p * halves + (u % halves);
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (d0 + k < T) {
+        const int64_t tp = tix ? tix[t_begin + d0 + k] : t_begin + d0 + k;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(src + tp * stride16 + so));
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (d0 + k < T) dst[(int64_t)(d0 + k) * n_units + u] = v[k];
+  }
+}
+}  // namespace
+
+extern "C" int ctb_pull_pack(const ctb_plan* P, const void* x, int dtype, int64_t stride,
+                             const int32_t* time_index, int64_t t_begin, int64_t T, void* dst, void* stream) {
+  if (!P || !x || (!dst && T > 0) || T < 0 || T >= (1ll << 31) || !P->compact) {
+    ctb_set_error("ctb_pull_pack: needs a compact plan and non-null buffers");
+    return CTB_ERR_INVALID;
+  }
+  if (dtype != CTB_F32 && dtype != CTB_F64) { ctb_set_error("dtype=%d unsupported", dtype); return CTB_ERR_INVALID; }
+  const int64_t es = dtype == CTB_F32 ? 4 : 8;
+  const int64_t phys_ncell = (int64_t)P->nlat_phys * P->nlon_phys;
+  if ((stride * es) % 16 != 0 || (uintptr_t)x % 16 != 0 || phys_ncell % CTB_PIECE != 0) {
+    ctb_set_error("ctb_pull_pack: planes must be 16-byte aligned and hold a multiple of 4 gridcells");
+    return CTB_ERR_UNSUPPORTED;
+  }
+  if (T == 0) return CTB_OK;
+  CtbDeviceGuard guard(P->device);
+  if (guard.err != cudaSuccess) { ctb_set_error("cudaSetDevice(%d) failed: %s", P->device, cudaGetErrorString(guard.err)); return CTB_ERR_CUDA; }
+  const int halves = (int)(es / 4);
+  const int n_units = (int)(P->ncell / CTB_PIECE) * halves;
+  const int64_t n_work = (int64_t)n_units * ((T + 3) / 4);
+  const unsigned grid = (unsigned)std::min<int64_t>((n_work + 255) / 256, 148 * 32);
+  pull_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(x), stride * es / 16, time_index, t_begin, (int)T, P->d_pack_src, n_units,
+      halves, static_cast<uint4*>(dst));
+  CTB_LAUNCH_CHECK();
   return CTB_OK;
 }

@@ -106,3 +106,14 @@ extern "C" int ctb_gather_rows(const ctb_plan* P, const void* x, int dtype, int 
   if (prev != P->device) cudaSetDevice(prev);
   return CTB_OK;
 }
+
+// Rows of a pitched DEVICE array to a pitched HOST array on `stream` (one DMA): the time-chunked
+// result copy of the host path -- out[:, :, t0:t1] of a [n_out*R][T] block -- overlaps the next chunk.
+extern "C" int ctb_copy_rows_to_host(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                                     size_t width_bytes, size_t rows, void* stream) {
+  if ((!dst || !src) && width_bytes * rows > 0) { ctb_set_error("ctb_copy_rows_to_host: null argument"); return CTB_ERR_INVALID; }
+  if (width_bytes * rows == 0) return CTB_OK;
+  CTB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+  return CTB_OK;
+}

@@ -1,16 +1,25 @@
 """Multi-GPU: the path shards along time (every day is independent given the plan).
 
-One process per GPU; each rank builds the (deterministic, ~5 MB) plan itself and
+One process per GPU; each rank builds the (deterministic, ~7 MB) plan itself and
 aggregates a contiguous block of days.  There is NO data-path collective; the only
-exchange is an optional final gather of the region x time outputs (NCCL all_gather over
+exchange is the optional final gather of the region x time outputs (NCCL all_gather over
 NVLink on GPUs, gloo in the CPU tests).  SURVEY.md section 8(e).
+
+* :func:`shard_range` / :func:`shard_sizes`   contiguous day blocks, multiples of the 32-day tile
+* :func:`all_gather_time`                     one collective + one strided copy into ``[.., T]``
+* :func:`aggregate_shard_overlapped`          device level: the shard is aggregated in time pieces and
+                                              the all_gather of piece k runs on a side stream while
+                                              the kernel of piece k+1 runs
+* :func:`aggregate_time_sharded`              Dataset level (any leading dims)
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_sizes", "all_gather_time", "aggregate_time_sharded"]
+__all__ = ["shard_range", "shard_sizes", "all_gather_time", "aggregate_shard_overlapped",
+           "aggregate_time_sharded"]
 
 
 def shard_sizes(T, world_size, align=32):
@@ -32,19 +41,104 @@ def shard_range(T, world_size, rank, align=32):
     return t0, t0 + sizes[rank]
 
 
+def _gather_padded(block, tmax, group):
+    """``block`` [M, n] (n <= tmax) from every rank -> [world, M, tmax] (columns >= n undefined)."""
+    world = dist.get_world_size(group)
+    M = block.shape[0]
+    if block.shape[1] == tmax and block.is_contiguous():
+        send = block
+    else:
+        send = torch.empty((M, tmax), dtype=block.dtype, device=block.device)
+        send[:, : block.shape[1]] = block
+    recv = torch.empty((world * M, tmax), dtype=block.dtype, device=block.device)   # concatenation along dim 0
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv.view(world, M, tmax)
+
+
+def _scatter_columns(full2d, recv, sizes, col0s, c0=0):
+    """full2d[:, col0s[r] + c0 : col0s[r] + c0 + sizes[r]] = recv[r, :, :sizes[r]] for every rank r:
+    ONE strided copy when the shards tile the row evenly, else one per rank."""
+    world = len(sizes)
+    pitch = full2d.shape[1] // world if world else 0
+    even = world > 0 and pitch * world == full2d.shape[1] and len(set(sizes)) == 1 and \
+        all(col0s[r] == r * pitch for r in range(world))
+    if even and sizes[0] > 0:
+        full2d.view(full2d.shape[0], world, pitch)[:, :, c0: c0 + sizes[0]].copy_(
+            recv[:, :, : sizes[0]].permute(1, 0, 2))
+        return
+    for r, n in enumerate(sizes):
+        if n > 0:
+            full2d[:, col0s[r] + c0: col0s[r] + c0 + n].copy_(recv[r, :, :n])
+
+
 def all_gather_time(local, T, group=None, align=32):
-    """Gather per-rank ``[n_out, R, T_local]`` blocks into ``[n_out, R, T]`` on every rank.
-    Ranks may hold different T_local (ragged last shard): blocks are padded to the largest
-    shard for the collective and trimmed after."""
+    """Gather per-rank ``[..., T_local]`` blocks (time LAST, any leading dims) into ``[..., T]`` on
+    every rank.  Ranks may hold different T_local (ragged last shards): one collective on blocks padded
+    to the largest shard, then the valid columns are copied straight into the final layout."""
     world = dist.get_world_size(group)
     sizes = shard_sizes(T, world, align)
+    lead = tuple(local.shape[:-1])
+    M = int(np.prod(lead)) if lead else 1
+    recv = _gather_padded(local.reshape(M, local.shape[-1]), max(sizes), group)
+    full = torch.empty((M, T), dtype=local.dtype, device=local.device)
+    _scatter_columns(full, recv, sizes, [sum(sizes[:r]) for r in range(world)])
+    return full.reshape(lead + (T,))
+
+
+def aggregate_shard_overlapped(plan, x0, x1, stride, T, kind="identity", params=(), n_out=1, group=None,
+                               pieces=4, gather=True, out=None):
+    """Time-sharded aggregation of device-resident TIME_MAJOR inputs with the output gather
+    overlapped: this rank aggregates days ``shard_range(T)`` of ``x0`` (``[T, stride]``, every rank
+    holds or views the same time axis) in ``pieces`` pieces; the ``all_gather`` of piece k runs on
+    a side stream while the kernel of piece k+1 runs, and lands through one strided copy in the
+    final ``[n_out, R, T]`` layout.  Returns ``(out, info)``; with ``gather=False`` only the local
+    block ``[n_out, R, T_local]``."""
+    from . import _engine as E
+    from . import _native as N
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = plan.device
+    sizes = shard_sizes(T, world)
+    col0 = [sum(sizes[:r]) for r in range(world)]
+    t0, tl = col0[rank], sizes[rank]
     tmax = max(sizes)
-    n_out, R = local.shape[0], local.shape[1]
-    pad = torch.zeros((n_out, R, tmax), dtype=local.dtype, device=local.device)
-    pad[:, :, : local.shape[2]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:, :, :n] for b, n in zip(bufs, sizes)], dim=2)
+    # piece boundaries inside a shard: the same on every rank (relative to the largest shard), 32-aligned
+    tiles = (tmax + 31) // 32
+    pieces = max(1, min(pieces, tiles))
+    cuts = [min(tmax, ((tiles * k) // pieces) * 32) for k in range(pieces)] + [tmax]
+    R, M = plan.R, n_out * plan.R
+    if gather and out is None:
+        out = torch.empty((n_out, R, T), dtype=torch.float64, device=dev)
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev) if gather else None
+    locs, done = [], []
+    for k in range(pieces):
+        c0, c1 = cuts[k], cuts[k + 1]
+        n = max(0, min(c1, tl) - c0)           # this rank's valid days in the piece
+        loc = torch.empty((n_out, R, c1 - c0), dtype=torch.float64, device=dev)
+        if n > 0:
+            a = x0[t0 + c0: t0 + c0 + n]
+            b = x1[t0 + c0: t0 + c0 + n] if x1 is not None else None
+            E.aggregate_device(plan, a, b, N.LAYOUT_TIME_MAJOR, stride, None, n, kind, params, n_out,
+                               out=loc, out_ld=c1 - c0)
+        locs.append(loc)
+        if gather:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                recv = torch.empty((world * M, c1 - c0), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(recv, loc.view(M, c1 - c0), group=group)
+                _scatter_columns(out.view(M, T), recv.view(world, M, c1 - c0),
+                                 [max(0, min(c1, s) - c0) for s in sizes], col0, c0)
+                recv.record_stream(side)
+                loc.record_stream(side)
+            done.append(side)
+    if not gather:
+        return torch.cat([l[:, :, : max(0, min(cuts[k + 1], tl) - cuts[k])] for k, l in enumerate(locs)], dim=2), \
+            {"t0": t0, "t1": t0 + tl}
+    main.wait_stream(side)
+    return out, {"t0": t0, "t1": t0 + tl, "pieces": pieces,
+                 "bytes_received": int(8 * M * (T - tl))}
 
 
 def aggregate_time_sharded(ds, variable, aggwt, agglev, weights, backup_aggwt="areawt", gather=True,
@@ -52,15 +146,14 @@ def aggregate_time_sharded(ds, variable, aggwt, agglev, weights, backup_aggwt="a
     """``weighted_aggregate_grid_to_regions`` over a process group: every rank aggregates its own
     contiguous block of days of ``ds`` (each rank holds, or lazily views, the same Dataset) on its
     own GPU with the replicated plan; with ``gather=True`` the region x time blocks are exchanged
-    once at the end (one all_gather) and every rank returns the full result, otherwise each rank
-    returns its block (what a job that writes per-rank files wants: 285 MB per rank and year-block
-    would otherwise cross NVLink for nothing).
+    once at the end (one all_gather per variable) and every rank returns the full result, otherwise
+    each rank returns its block (what a job that writes per-rank files wants: 285 MB per rank and
+    year-block would otherwise cross NVLink for nothing).  Variables may carry leading dims
+    (ensemble member, model): everything but ``time_dim`` rides along.
 
     ``aggregate_fn`` (tests) replaces the single-GPU aggregation; it must have the signature of
     ``weighted_aggregate_grid_to_regions``.
     """
-    import numpy as np
-
     from ._xr import Dataset, Variable, from_any
     if aggregate_fn is None:
         from .aggregations.aggregations import weighted_aggregate_grid_to_regions as aggregate_fn
@@ -81,13 +174,12 @@ def aggregate_time_sharded(ds, variable, aggwt, agglev, weights, backup_aggwt="a
     out = Dataset()
     for name in names:
         v = local._vars[name]
-        ax_t, ax_r = v.dims.index(time_dim), v.dims.index(agglev)
+        ax_t = v.dims.index(time_dim)
         a = v.physical if isinstance(v.physical, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v.values))
         if backend == "nccl" and not a.is_cuda:
             a = a.cuda()
-        blk = a.permute(ax_r, ax_t).contiguous()[None]                    # [1, R, T_local]
-        full = all_gather_time(blk, T, group)[0]                          # [R, T]
-        full = full if (ax_r, ax_t) == (0, 1) else full.t()
+        blk = a.movedim(ax_t, -1).contiguous()                            # [..., T_local]
+        full = all_gather_time(blk, T, group).movedim(-1, ax_t)           # back to the variable's dim order
         out[name] = Variable(v.dims, full if full.is_cuda else full.numpy(), v.attrs)
     out._coords[agglev] = local._coords[agglev]
     for d, c in ds._coords.items():

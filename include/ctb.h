@@ -179,6 +179,19 @@ int ctb_gather_rows(const ctb_plan* plan, const void* x, int dtype, int layout, 
 int ctb_host_pack(const ctb_plan* plan, const void* x, int dtype, int64_t stride,
                   const int64_t* time_index, int64_t t_begin, int64_t T, void* dst, int n_threads);
 
+/* The same packing done by the GPU: x is a HOST array in pinned, device-accessible memory
+ * (cudaHostAlloc / cudaHostRegister); the referenced pieces are read over PCIe by a kernel on `stream`
+ * and written to dst[T][n_packed_cells] in DEVICE memory.  No host core touches the data (ranks of a
+ * multi-GPU job share the host's cores, not its PCIe links).  time_index: DEVICE int32, nullable.
+ * Planes must be 16-byte aligned and hold a multiple of 4 gridcells (else CTB_ERR_UNSUPPORTED). */
+int ctb_pull_pack(const ctb_plan* plan, const void* x, int dtype, int64_t stride, const int32_t* time_index,
+                  int64_t t_begin, int64_t T, void* dst, void* stream);
+
+/* rows of a pitched DEVICE array -> pitched HOST (pinned) array, one asynchronous 2-D copy on `stream`:
+ * the host path returns out[:, :, t0:t1] of a finished time chunk while the next chunk is in flight */
+int ctb_copy_rows_to_host(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                          size_t rows, void* stream);
+
 /* ---- fused time reduction (annual sums of the daily region values) -------- *
  * The step after the path in CIL pipelines: EDD_P = sum over the days of a period of the
  * aggregated EDD_d (transformations.py:17-21).  group_of_day (HOST int32[T]) gives the output

@@ -116,3 +116,50 @@ def test_aggregate_time_sharded_api_world2():
         p.join(60)
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
+
+
+def _oracle_aggregate_nd(ds, variable, aggwt, agglev, weights=None, backup_aggwt="areawt", **kw):
+    import oracle
+    from climate_toolbox_b200 import Dataset
+    x = ds[variable].values
+    out, rd, labels = oracle.weighted_aggregate_grid_to_regions(
+        x, ds[variable].dims, ds["lat"].values, ds["lon"].values, weights, aggwt, agglev, backup_aggwt)
+    return Dataset({variable: (rd, out)}, coords={"time": ds["time"].values, "model": ds["model"].values,
+                                                  agglev: labels})
+
+
+def _worker_leading_dims(rank, world, port, T, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from climate_toolbox_b200 import Dataset, synthetic
+        from climate_toolbox_b200.parallel import aggregate_time_sharded
+        lat, lon = synthetic.grid_labels(4.0)
+        df = synthetic.weights_table(4.0, 60, seed=2)
+        tas, _, _ = synthetic.tas_field(3 * T, len(lat), len(lon), seed=1, dtype=np.float64)
+        x = tas.reshape(3, T, len(lat), len(lon))
+        dims = ("model", "time", "lat", "lon")
+        ds = Dataset({"tas": (dims, x)}, coords={"model": ["a", "b", "c"], "time": np.arange(T), "lat": lat, "lon": lon})
+        full = aggregate_time_sharded(ds, "tas", "popwt", "hierid", df, aggregate_fn=_oracle_aggregate_nd)
+        ref, rd, _ = oracle.weighted_aggregate_grid_to_regions(x, dims, lat, lon, df, "popwt", "hierid")
+        ok = full["tas"].dims == rd == ("model", "time", "hierid") and \
+            np.array_equal(full["tas"].values, ref, equal_nan=True)
+        q.put((rank, bool(ok), tuple(full["tas"].shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_aggregate_time_sharded_leading_dims_world2():
+    """A variable with a leading (model) dim: everything but the time dim rides along in the gather."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_leading_dims, args=(r, 2, port, 70, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res

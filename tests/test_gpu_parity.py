@@ -184,8 +184,8 @@ def test_config1_shape_areawt(where, variant):
     check(out.tas.values, ref, scale)
 
 
-@pytest.mark.parametrize("mode", ["packed_pageable", "packed_pinned_leap", "zero_copy_pinned",
-                                  "chunked_pinned", "chunked_pageable"])
+@pytest.mark.parametrize("mode", ["packed_pageable", "packed_pinned_leap", "pulled_pinned_leap", "pulled_pinned",
+                                  "zero_copy_pinned", "chunked_pinned", "chunked_pageable"])
 def test_host_input_paths(mode):
     """Host arrays.  Default: a compact plan -- the referenced gridcells are packed on the host
     (ctb_host_pack) and only they cross PCIe.  Alternatives: whole time chunks copied
@@ -205,14 +205,16 @@ def test_host_input_paths(mode):
         exp_in = tas[tix]
     T = exp_in.shape[0]
     grid = E.GridSpec(lat, lon)
-    plan = E.get_plan(grid, df, "areawt", "hierid", compact=mode.startswith("packed"))
-    if mode.startswith("packed"):
+    compact = mode.startswith("packed") or mode.startswith("pulled")
+    plan = E.get_plan(grid, df, "areawt", "hierid", compact=compact)
+    if compact:
         # referenced pieces + padding of every run to a 64-byte boundary of the packed plane
         assert 4 * plan.info["n_pieces_distinct"] <= plan.info["n_packed_cells"] < len(lat) * len(lon)
         assert plan.info["n_packed_cells"] % 16 == 0
     n0 = E.launch_count()
     out = E.aggregate_host(plan, [arr.reshape(70, -1)], N.LAYOUT_TIME_MAJOR, arr.shape[1] * arr.shape[2],
-                           tix, T, chunk_bytes=1 << 20, zero_copy=(mode == "zero_copy_pinned"))
+                           tix, T, chunk_bytes=1 << 20, zero_copy=(mode == "zero_copy_pinned"),
+                           ingest="pull" if mode.startswith("pulled") else "pack")
     assert (E.launch_count() - n0 == 1) == (mode == "zero_copy_pinned")
     ref, rd, labels, scale = oracle_agg(exp_in, ("time", "lat", "lon"), lat, lon, df, "areawt", "hierid")
     check(out[0].cpu().numpy().T, ref, scale)
