@@ -47,9 +47,9 @@ WORKLOADS = {
 YEARS_PER_STEP, POOL, ENSEMBLE_YEARS = 8, 4, 21 * 2 * 95
 METRIC = "region-days/sec"
 PARAMS = {"identity": (), "poly": (273.15, 1, 2, 3, 4), "edd": (283.15, 303.15)}
-KERNEL = {"identity": "agg_stream_kernel", "poly": "agg_stream_kernel", "edd": "agg_snyder_kernel"}
+KERNEL = {"identity": "agg_stream_kernel", "poly": "agg_stream_kernel", "edd": "agg_stream_kernel"}
 # fp64-pipe instructions per CSR entry and day of the Snyder kernel (2 thresholds), counted in the SASS of
-# agg_snyder_kernel<float, EDD, 2> (profiles/r2_sass_histograms.md); 64 fp64 lanes per SM and clock
+# agg_stream_kernel<float, EDD, 2> (profiles/r2_sass_histograms.md); 64 fp64 lanes per SM and clock
 SNYDER_FP64_OPS_PER_ENTRY_DAY = 118
 FP64_LANES_PER_SM_CLK = 64
 
@@ -516,12 +516,11 @@ def run_ours(args):
     if world > 1 and not streaming and kind == "identity":
         from climate_toolbox_b200.parallel import aggregate_shard_overlapped, shard_sizes
         x = xs[0]
-        full = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
 
         def run(gather, pieces):
             def f():
                 aggregate_shard_overlapped(plan, x, None, ncell, T, kind, PARAMS[kind], n_out, pieces=pieces,
-                                           gather=gather, out=full if gather else None)
+                                           gather=gather)
             return f
 
         s_steps = max(3, min(args.steps, 10))
@@ -537,7 +536,7 @@ def run_ours(args):
                   "value": plan.R * T / (ovl_ms * 1e-3), "value_compute_only": plan.R * T / (comp_ms * 1e-3),
                   "unit": "region-days/s", "scaling": "strong",
                   "limiter": "the fp64 all_gather: every rank receives (N-1)/N of the 285 MB output over NVLink"}
-        del full
+        plan.__dict__.pop("_shard_buffers", None)
 
     # ---- the other configs and input variants (N = 1: device-timed, 10 steps each) ----
     also = None

@@ -1,12 +1,6 @@
-// Dispatch of ctb_aggregate / ctb_aggregate_grouped, and the kernels that are not the
-// streaming kernel (ctb_stream.cu):
+// Dispatch of ctb_aggregate / ctb_aggregate_grouped, and the kernels beside the streaming kernel
+// (ctb_stream.cu, every TIME_MAJOR input whose planes are 16-byte aligned):
 //
-//   agg_snyder_kernel  TIME_MAJOR (tasmin, tasmax) -> Snyder EDD / GDD fused into the gather
-//                      (transformations.py:69-89, 139-141 + aggregations.py:27, 75-82).  fp64
-//                      ALU bound: CTAs of 8 warps with up to 128 registers, two per SM; the
-//                      footprint is staged with 16-byte loads through registers into a
-//                      TRANSPOSED tile sx[input][cell][day] (row stride 33 => conflict-free);
-//                      one warp per region, lane = day, regions taken from a shared counter.
 //   agg_direct_kernel  CELL_MAJOR input [lat][lon][T] (the reference test fixture), and the
 //                      fallback for planes that are not 16-byte aligned: one warp per
 //                      (region, 32-day tile), lane = day.
@@ -24,45 +18,6 @@ namespace {
 
 template <int KIND>
 struct NIn { static constexpr int v = (KIND == CTB_TR_EDD || KIND == CTB_TR_GDD) ? 2 : 1; };
-
-// ---- mbarrier + bulk async copy (TMA 1-D; SASS: UBLKCP / SYNCS) ---------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n"
-      "@p bra DONE_%=;\n"
-      "nanosleep.u32 128;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-template <typename T>
-__device__ __forceinline__ T lds_val(uint32_t addr) {
-  T v;
-  if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
-  return v;
-}
 
 // one CSR entry: acc_j += w * f_j(x), NaN products skipped (skipna sum, aggregations.py:78)
 template <typename TIN, int KIND, int NOUT>
@@ -84,189 +39,6 @@ __device__ __forceinline__ void lane_group(const AggArgs& a, int t, bool valid, 
     tg = valid ? __ldg(a.tgroup + a.t_off + t) : -1;
     tg0 = __shfl_sync(0xffffffffu, tg, 0);
   }
-}
-
-template <typename TIN, int KIND, int NOUT, bool VEC, int THREADS>
-__global__ void __launch_bounds__(THREADS, 2) agg_snyder_kernel(const AggArgs a) {
-  constexpr int NIN = NIn<KIND>::v;
-  constexpr int TILE_LOADS = 8;                 // 16-byte loads per thread in flight
-  constexpr int S = CTB_S;
-  constexpr int HALVES = sizeof(TIN) / 4;       // 16-byte units per piece-day of one input
-  constexpr int CPU = 16 / sizeof(TIN);         // cells per unit
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_unit;
-  __shared__ int s_seg_next;   // next region of the tile nobody has taken yet
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned char* const s_blob = smem_raw + a.tile_stride;
-  if (tid == 0) mbar_init(&s_bar, 1);
-
-  // Work unit = (bundle, chunk of `chunk_tb` consecutive 32-day blocks), handed out by an
-  // atomic counter in chunk-major order; the bundle's metadata is fetched once per unit.
-  for (int n_done = 0;; ++n_done) {
-    __syncthreads();   // previous unit fully reduced: tile, blob and s_unit may be reused
-    if (tid == 0) {
-      s_unit = atomicAdd(a.work_counter, 1);
-      if (s_unit < a.n_items) {
-        const int4 d = __ldg(a.b_desc + s_unit % a.n_bundles);
-        const int64_t o = ((int64_t)(uint32_t)d.y << 32) | (uint32_t)d.x;
-        bulk_g2s(s_blob, a.blob + o, (uint32_t)d.z, &s_bar);
-      }
-    }
-    __syncthreads();
-    const int unit = s_unit;
-    if (unit >= a.n_items) break;
-    const int tb_begin = (unit / a.n_bundles) * a.chunk_tb;
-    const int tb_end = min(tb_begin + a.chunk_tb, a.n_tb);
-    mbar_wait(&s_bar, n_done & 1);
-    const CtbBlobHeader H = *reinterpret_cast<const CtbBlobHeader*>(s_blob);
-    const int* s_piece = reinterpret_cast<const int*>(s_blob + sizeof(CtbBlobHeader));
-    const unsigned char* mb = s_blob + H.bytes_a;
-    const int nP = H.n_pieces;
-
-    for (int tb = tb_begin; tb < tb_end; ++tb) {
-      const int t0 = tb * CTB_TB;
-      if (tb != tb_begin) __syncthreads();   // tile buffer free again
-      if (tid == 0) s_seg_next = 0;
-      // ---------------- stage: [day][piece] global  ->  [input][cell][day] shared -------------
-      {
-        const int l8 = lane & 7, l4 = lane >> 3;
-        const int dl = (warp & 7) * 4 + l4;            // day within the tile
-        constexpr int NSUB = (THREADS / 32) / 8;       // warps sharing one 4-day group
-        const int sub = warp >> 3;
-        const int t = t0 + dl;
-        const int nPH = nP * HALVES;
-        const int n_units = nPH * NIN;                 // unit index: [input][piece][half]
-        if (t < a.T) {
-          const int64_t tp = a.tix ? a.tix[t] : t;
-          const TIN* p0 = reinterpret_cast<const TIN*>(a.x0) + tp * a.stride;
-          const TIN* p1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) + tp * a.stride : p0;
-          asm volatile("" : "+l"(p0));   // keep the day's base pointers in registers
-          if constexpr (NIN == 2) asm volatile("" : "+l"(p1));
-          TIN* sx = reinterpret_cast<TIN*>(smem_raw) + dl;
-          for (int g0 = l8 + 8 * sub; g0 < n_units; g0 += 8 * NSUB * TILE_LOADS) {
-            int off[TILE_LOADS];
-            uint32_t v[TILE_LOADS][4];
-#pragma unroll
-            for (int u = 0; u < TILE_LOADS; ++u) {      // all index reads first, then all loads
-              const int g = g0 + 8 * NSUB * u;
-              if (g < n_units) {
-                const int in = (NIN == 2 && g >= nPH) ? 1 : 0, r = g - (in ? nPH : 0);
-                off[u] = s_piece[r / HALVES] * CTB_PIECE + (r % HALVES) * CPU;
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < TILE_LOADS; ++u) {
-              const int g = g0 + 8 * NSUB * u;
-              if (g < n_units) {
-                const TIN* src = (NIN == 2 && g >= nPH) ? p1 + off[u] : p0 + off[u];
-                if constexpr (VEC) {
-                  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                               : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "l"(src));
-                } else {
-                  TIN tv[CPU];
-#pragma unroll
-                  for (int q = 0; q < CPU; ++q) tv[q] = (off[u] + q < a.ncell) ? __ldg(src + q) : TIN(0);
-                  if constexpr (sizeof(TIN) == 4) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[u][q] = __float_as_uint((float)tv[q]);
-                  } else {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                      const long long bb = __double_as_longlong((double)tv[q]);
-                      v[u][2 * q] = (uint32_t)bb; v[u][2 * q + 1] = (uint32_t)(bb >> 32);
-                    }
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < TILE_LOADS; ++u) {
-              const int g = g0 + 8 * NSUB * u;
-              if (g < n_units) {
-                // unit g covers cells [g*CPU, g*CPU + CPU) of the [input][cell] row space
-                TIN* sd = sx + (size_t)g * CPU * S;
-                if constexpr (sizeof(TIN) == 4) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) sd[q * S] = __uint_as_float(v[u][q]);
-                } else {
-#pragma unroll
-                  for (int q = 0; q < 2; ++q)
-                    sd[q * S] = __longlong_as_double(((long long)v[u][2 * q + 1] << 32) | v[u][2 * q]);
-                }
-              }
-            }
-          }
-        }
-      }
-      __syncthreads();
-
-      // ---------------- gather + segmented weighted sum: warp = region, lane = day ------------
-      const CtbSeg* segs = reinterpret_cast<const CtbSeg*>(mb + H.off_seg);
-      const CtbEnt* ENT = reinterpret_cast<const CtbEnt*>(mb + H.off_ent);
-      const uint32_t sb0 = smem_u32(smem_raw) + lane * (uint32_t)sizeof(TIN);
-      const uint32_t sb1 = sb0 + (uint32_t)(nP * CTB_PIECE * S) * (uint32_t)sizeof(TIN);
-      const int t = t0 + lane;
-      const bool valid = t < a.T;
-      int tg, tg0;
-      lane_group(a, t, valid, tg, tg0);
-      // the planner's column offsets are row-major (column * elem_bytes): x 33 for this tile
-      auto at0 = [&](uint32_t o) { return lds_val<TIN>(sb0 + o * (uint32_t)S); };
-      auto at1 = [&](uint32_t o) { return lds_val<TIN>(sb1 + o * (uint32_t)S); };
-      for (int s = warp; s < H.n_seg;) {
-        const CtbSeg sg = segs[s];
-        double acc[NOUT], acc2[NOUT];
-#pragma unroll
-        for (int j = 0; j < NOUT; ++j) acc[j] = acc2[j] = 0.0;
-        // Quads of entries, software-pipelined: the metadata and the staged values of quad c+1
-        // are loaded before quad c is accumulated.  The padding of the last quad has weight 0
-        // and is masked out (0 * NaN must not reach the sum).
-        const int e0 = (int)sg.e0_4 * 4;
-        const int n_chunks = ((int)sg.n + 3) >> 2;
-        const int last_valid = (int)sg.n - 4 * (n_chunks - 1);   // 1..4 entries in the last quad
-        double wA[4];
-        TIN xA[4], yA[4];
-        auto fetch = [&](int e, double (&w)[4], TIN (&x0)[4], TIN (&x1)[4]) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 m = *reinterpret_cast<const uint4*>(ENT + e + q);
-            w[q] = __hiloint2double((int)m.y, (int)m.x);
-            x0[q] = at0(m.z);
-            x1[q] = at1(m.z);
-          }
-        };
-        if (n_chunks > 0) fetch(e0, wA, xA, yA);
-        for (int c = 0; c < n_chunks; ++c) {
-          double wB[4];
-          TIN xB[4], yB[4];
-          const bool more = c + 1 < n_chunks;
-          if (more) fetch(e0 + 4 * (c + 1), wB, xB, yB);
-          if (more || last_valid == 4) {
-            accumulate<TIN, KIND, NOUT>(a.tr, wA[0], xA[0], yA[0], acc);
-            accumulate<TIN, KIND, NOUT>(a.tr, wA[1], xA[1], yA[1], acc2);
-            accumulate<TIN, KIND, NOUT>(a.tr, wA[2], xA[2], yA[2], acc);
-            accumulate<TIN, KIND, NOUT>(a.tr, wA[3], xA[3], yA[3], acc2);
-          } else {
-            accumulate<TIN, KIND, NOUT>(a.tr, wA[0], xA[0], yA[0], acc);
-            if (last_valid > 1) accumulate<TIN, KIND, NOUT>(a.tr, wA[1], xA[1], yA[1], acc2);
-            if (last_valid > 2) accumulate<TIN, KIND, NOUT>(a.tr, wA[2], xA[2], yA[2], acc);
-          }
-          if (more) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { wA[q] = wB[q]; xA[q] = xB[q]; yA[q] = yB[q]; }
-          }
-        }
-        double v[NOUT];
-#pragma unroll
-        for (int j = 0; j < NOUT; ++j) v[j] = acc[j] + acc2[j];
-        ctb_emit<NOUT>(a, sg.target, sg.rden, v, lane, t, valid, tb, tg, tg0);
-        int nx = 0;
-        if (lane == 0) nx = (THREADS / 32) + atomicAdd(&s_seg_next, 1);
-        s = __shfl_sync(0xffffffffu, nx, 0);
-      }
-    }   // tiles of the unit
-  }   // units
 }
 
 // Regions split over several bundles (and regions with no kept rows):
@@ -357,52 +129,6 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(const AggArgs a) {
 
 // ------------------------------------------------------------- dispatch -----
 template <typename TIN, int KIND, int NOUT>
-int launch_snyder(const ctb_plan* P, AggArgs a, bool vec, cudaStream_t st) {
-  constexpr int NIN = NIn<KIND>::v;
-  constexpr int THREADS = 256;
-  static int n_sm[64] = {0};
-  static bool attr_set[64][2] = {{false}};
-  const int dev = P->device & 63;
-  const size_t tile = ((size_t)NIN * P->info.max_bundle_cells * CTB_S * sizeof(TIN) + 127) & ~(size_t)127;
-  const size_t smem = tile + CTB_META_CAP;
-  const size_t smem_cap = 164 * 1024 / CTB_CTAS_PER_SM - 1024 - 512;
-  if (smem > smem_cap) {
-    ctb_set_error("plan's bundles need %zu bytes of staging (cap %zu): build it with stage_bytes = n_in * elem_bytes",
-                  smem, smem_cap);
-    return CTB_ERR_UNSUPPORTED;
-  }
-  if (!n_sm[dev]) CTB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, P->device));
-  const int n_tb = (a.T + CTB_TB - 1) / CTB_TB;
-  int chunk_tb = 4;
-  const int n_chunks = (n_tb + chunk_tb - 1) / chunk_tb;
-  chunk_tb = n_chunks ? (n_tb + n_chunks - 1) / n_chunks : 1;
-  const int64_t n_units = (int64_t)P->n_bundles * n_chunks;
-  if (n_units >= (1ll << 31)) { ctb_set_error("too many work units"); return CTB_ERR_UNSUPPORTED; }
-  a.n_bundles = P->n_bundles; a.n_items = (int)n_units; a.n_tb = n_tb; a.chunk_tb = std::max(chunk_tb, 1);
-  a.tile_stride = (int)tile;
-  a.work_counter = P->d_work_counter + P->work_counter_slot.fetch_add(1) % CTB_N_WORK_COUNTERS;
-  if (n_units > 0) {
-    const unsigned grid = (unsigned)std::min<int64_t>(n_units, (int64_t)n_sm[dev] * CTB_CTAS_PER_SM);
-    CTB_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
-    auto go = [&](auto k) -> int {
-      if (!attr_set[dev][vec ? 1 : 0]) {
-        // 164 KB of shared memory per SM: the L1 that is left holds the loads in flight
-        CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 72));
-        attr_set[dev][vec ? 1 : 0] = true;
-      }
-      k<<<grid, THREADS, smem, st>>>(a);
-      return CTB_OK;
-    };
-    const int rc = vec ? go(agg_snyder_kernel<TIN, KIND, NOUT, true, THREADS>)
-                       : go(agg_snyder_kernel<TIN, KIND, NOUT, false, THREADS>);
-    if (rc) return rc;
-    CTB_LAUNCH_CHECK();
-  }
-  return CTB_OK;
-}
-
-template <typename TIN, int KIND, int NOUT>
 int launch_direct(const AggArgs& a, int layout, cudaStream_t st) {
   AggArgs b = a;
   b.n_tb = (a.T + CTB_TB - 1) / CTB_TB;
@@ -417,12 +143,12 @@ int launch_direct(const AggArgs& a, int layout, cudaStream_t st) {
   return CTB_OK;
 }
 
-// variant 1 = staged (streaming kernel for IDENTITY / POLY, Snyder kernel for EDD / GDD), 2 = direct
+// variant 1 = the streaming kernel (ctb_stream.cu), 2 = direct
 template <typename TIN, int KIND, int NOUT>
 int run(const ctb_plan* P, const AggArgs& a, int layout, int variant, bool vec, cudaStream_t st) {
+  (void)vec;
   if (variant == 2) return launch_direct<TIN, KIND, NOUT>(a, layout, st);
-  if constexpr (KIND == CTB_TR_EDD || KIND == CTB_TR_GDD) return launch_snyder<TIN, KIND, NOUT>(P, a, vec, st);
-  else return ctb_launch_stream(P, a, std::is_same<TIN, float>::value ? CTB_F32 : CTB_F64, KIND, NOUT, st);
+  return ctb_launch_stream(P, a, std::is_same<TIN, float>::value ? CTB_F32 : CTB_F64, KIND, NOUT, st);
 }
 
 template <typename TIN, int KIND>
@@ -487,22 +213,21 @@ int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype,
   const size_t es = dtype == CTB_F32 ? 4 : 8;
   const bool vec = (P->ncell % CTB_PIECE == 0) && ((stride * es) % 16 == 0) &&
                    ((uintptr_t)x0 % 16 == 0) && (!x1 || (uintptr_t)x1 % 16 == 0);
-  const bool snyder = transform == CTB_TR_EDD || transform == CTB_TR_GDD;
   // the streaming kernel copies 16-byte units: planes that are not 16-byte aligned take the direct kernel
-  if (variant == 1 && !snyder && !vec) variant = 2;
-  if (variant == 1 && P->elem_bytes != (int)es) {
+  if (variant == 1 && !vec) variant = 2;
+  if (variant != 2 && P->elem_bytes != (int)es) {
     ctb_set_error("plan was built for %d-byte elements, input has %d-byte elements: rebuild it with "
                   "elem_bytes=%d", P->elem_bytes, (int)es, (int)es);
     return CTB_ERR_UNSUPPORTED;
   }
-  if (variant == 1 && P->stage_bytes < ctb_tr_nin(transform) * (int)es) {
+  if (variant != 2 && P->stage_bytes < ctb_tr_nin(transform) * (int)es) {
     ctb_set_error("plan stages %d bytes per gridcell-day, the transform needs %d: rebuild it with "
                   "stage_bytes_per_cell_day=%d", P->stage_bytes, ctb_tr_nin(transform) * (int)es,
                   ctb_tr_nin(transform) * (int)es);
     return CTB_ERR_UNSUPPORTED;
   }
   // workspace: [partial rows of split regions][per-tile partial sums of the time reduction]
-  const size_t need_s = variant == 1 ? scratch_bytes(P, G ? G->T : T, n_out) : 0;
+  const size_t need_s = variant != 2 ? scratch_bytes(P, G ? G->T : T, n_out) : 0;
   const size_t need_g = G ? gpart_bytes(P, G, n_out) : 0;
   if (need_s + need_g > 0 && (!workspace || workspace_bytes < need_s + need_g)) {
     ctb_set_error("workspace of %zu bytes required, got %zu", need_s + need_g, workspace ? workspace_bytes : (size_t)0);
@@ -543,7 +268,7 @@ int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype,
     agg_group_finish_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(a, n_out);
     CTB_LAUNCH_CHECK();
   }
-  if (variant == 1 && P->n_split > 0) {
+  if (variant != 2 && P->n_split > 0) {
     const int64_t cols = G ? G->n_groups : T;
     const dim3 g2(P->n_split, (unsigned)std::min<int64_t>((cols + 255) / 256, 64));
     agg_fixup_kernel<<<g2, 256, 0, st>>>(a, n_out);

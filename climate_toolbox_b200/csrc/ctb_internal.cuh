@@ -35,7 +35,7 @@ extern std::atomic<int64_t> g_ctb_launches;
 
 // ------------------------------------------------------------- constants ---
 constexpr int CTB_TB = 32;             // days per staging tile
-constexpr int CTB_S = CTB_TB + 1;      // transposed tile (Snyder kernel): row stride in elements, odd => conflict-free
+constexpr int CTB_S = CTB_TB + 1;      // planner's tile budget unit (see CTB_TILE_BYTES)
 constexpr int CTB_PIECE = 4;           // gridcells per staged piece (16 B of f32)
 
 // Per-bundle metadata blob (one cp.async.bulk into shared memory per work unit):
@@ -82,11 +82,9 @@ constexpr int CTB_STREAM_TILE_BYTES = CTB_TB * CTB_ROWB;           // 66,048 B p
 constexpr int CTB_STREAM_THREADS = 1024;
 constexpr int CTB_STREAM_PRODUCER_WARPS = 4;
 
-// ---- Snyder kernel (ctb_agg.cu): transposed tiles [cell][day], CTAs of 8 warps, two per SM.
-// Shared memory is deliberately limited to 164 KB per SM: it is carved out of the L1, and the
-// L1 that is left bounds the register-staged loads in flight (bench_micro/stage_bw3.py).
-constexpr int CTB_TILE_BYTES = CTB_TILE_UNITS * 4 * CTB_S * 4;    // 67,584 B of shared memory
-constexpr int CTB_CTAS_PER_SM = 2;
+// the planner sizes bundles against this budget: 128 pieces x 4 cells x 33 x 4 bytes (the round-1
+// tile; kept because it fixes the bundle sizes the kernels are tuned for: n_pieces * stage_bytes <= 512)
+constexpr int CTB_TILE_BYTES = CTB_TILE_UNITS * 4 * CTB_S * 4;    // 67,584
 constexpr int CTB_N_WORK_COUNTERS = 64;
 
 // -------------------------------------------------------------- the plan ---
@@ -182,6 +180,28 @@ __device__ __forceinline__ double ctb_ipow(double d, int p) {
 // (half of the instructions of the Snyder kernels).
 static __constant__ double ctb_edd_H[CTB_EDD_H_N] = CTB_EDD_H_COEFFS;
 
+// 1/w and sqrt(v) of the Snyder form: the hardware's fp64 seeds (rcp.approx / rsqrt.approx: ONE
+// special-function instruction each, MUFU.RCP64H / MUFU.RSQ64H, 2^-23) refined by two fp64 Newton
+// steps (to 1e-16): 5 + 7 instructions instead of the ~20 + ~34 of the IEEE-rounded division and
+// square-root sequences with their slow-path calls -- half of the instructions of an evaluation in
+// the SASS of the round-2 kernel.  (Seeds from the SINGLE-precision unit were measured slower: each
+// f64<->f32 conversion is another XU instruction.)
+__device__ __forceinline__ double ctb_rcp_pos(double w) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+  r = fma(r, fma(-w, r, 1.0), r);
+  return fma(r, fma(-w, r, 1.0), r);     // w = 0 / inf / NaN: NaN or inf, only used by unselected forms
+}
+__device__ __forceinline__ double ctb_sqrt01(double v) {   // v in [0, 1] (or NaN)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+  const double h = 0.5 * y;
+  double s = v * y;
+  s = fma(fma(-s, s, v), h, s);
+  s = fma(fma(-s, s, v), h, s);
+  return v > 0.0 ? s : v;                                  // v = 0: 0 (not 0 * inf); NaN stays NaN
+}
+
 __device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
   const double v = 1.0 - a;
   const double t = fma(2.0, v, -1.0);
@@ -194,7 +214,7 @@ __device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
   for (int k = 14; k >= 0; k -= 2) pe = fma(pe, t2, ctb_edd_H[k]);
 #pragma unroll
   for (int k = 13; k >= 1; k -= 2) po = fma(po, t2, ctb_edd_H[k]);
-  return v * sqrt(v) * fma(po, t, pe);
+  return v * ctb_sqrt01(v) * fma(po, t, pe);
 }
 
 __device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double rW,
@@ -235,11 +255,11 @@ __device__ __forceinline__ void ctb_apply(const CtbTr& P, double x0, double x1, 
       for (int j = 0; j < NOUT; ++j) f[j] = ctb_ipow(d, P.ip[j]);
     }
   } else if constexpr (KIND == CTB_TR_EDD) {
-    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2, rW = 1.0 / W;
+    const double M = (x1 + x0) * 0.5, W = (x1 - x0) * 0.5, rW = ctb_rcp_pos(W);
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) f[j] = ctb_edd(x0, x1, M, W, rW, P.a[j]);
   } else {  // GDD
-    const double M = (x1 + x0) / 2, W = (x1 - x0) / 2, rW = 1.0 / W;
+    const double M = (x1 + x0) * 0.5, W = (x1 - x0) * 0.5, rW = ctb_rcp_pos(W);
 #pragma unroll
     for (int j = 0; j < NOUT; ++j)
       f[j] = ctb_edd(x0, x1, M, W, rW, P.a[2 * j]) - ctb_edd(x0, x1, M, W, rW, P.a[2 * j + 1]);
@@ -269,7 +289,7 @@ struct AggArgs {
   int n_stages;      // streaming kernel: tile stages in shared memory
   int n_tb;          // time blocks: ceil(T / 32)
   int chunk_tb;      // time blocks per work unit (a CTA keeps one bundle for a whole unit)
-  int* work_counter; // Snyder kernel: device counter for dynamic unit scheduling (zeroed per launch)
+  int* work_counter; // {next unit, CTAs done}: dynamic unit scheduling, re-armed by the kernel
   int knobs;         // experiments only (compiled in with -DCTB_EXPERIMENT): 1 = skip the copies, 4 = skip the reduction
   // fused time reduction (ctb_aggregate_grouped): the launch covers days [t_off, t_off + T) of the
   // groups' time axis; day t adds into output column tgroup[t_off + t]

@@ -647,9 +647,9 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   if ((rc = upload(&P->d_blob, B.blob))) return rc;
   if ((rc = upload(&P->d_b_desc, B.desc))) return rc;
   if ((rc = upload(&P->d_unit_tab, B.unit_tab))) return rc;
-  // [0, N): Snyder kernel (zeroed per launch); [N, 2N): streaming kernel's self-re-arming pairs
-  CTB_CUDA(cudaMalloc((void**)&P->d_work_counter, 2 * CTB_N_WORK_COUNTERS * sizeof(int)));
-  CTB_CUDA(cudaMemset(P->d_work_counter, 0, 2 * CTB_N_WORK_COUNTERS * sizeof(int)));
+  // {next unit, CTAs done} pairs of the streaming kernel: zero between launches (self re-arming)
+  CTB_CUDA(cudaMalloc((void**)&P->d_work_counter, CTB_N_WORK_COUNTERS * sizeof(int)));
+  CTB_CUDA(cudaMemset(P->d_work_counter, 0, CTB_N_WORK_COUNTERS * sizeof(int)));
   if ((rc = upload(&P->d_split_region, split_region))) return rc;
   if ((rc = upload(&P->d_split_slot_ptr, split_slot_ptr))) return rc;
   P->n_bundles = (int32_t)B.b_blob_off.size() - 1;

@@ -54,8 +54,22 @@ constexpr int NP = CTB_STREAM_PRODUCER_WARPS;
 #ifndef CTB_STAGES
 #define CTB_STAGES 3
 #endif
-constexpr int NG = CTB_TILE_UNITS / 8;        // groups of 8 units (128 bytes of a tile row)
+constexpr int NG = CTB_TILE_UNITS / 8;        // groups of 8 units (128 bytes of a tile row), all inputs together
 constexpr int UPW = (NG + NP - 1) / NP;       // ... per producer warp
+
+// Tile geometry.  A stage holds NIN input tiles of 32 day rows; one input's row has room for
+// 128 / NIN 16-byte units (the planner sizes the bundles of a two-input plan to half the cells) plus
+// 16 bytes, so that the row pitch is == 16 (mod 128) either way.
+template <int NIN>
+struct Geo {
+  static constexpr int UNITS = CTB_TILE_UNITS / NIN;
+  static constexpr int ROWB = UNITS * 16 + 16;        // 2,064 / 1,040 bytes
+  static constexpr int IN_BYTES = CTB_TB * ROWB;      // one input's tile
+  static constexpr int TILE_BYTES = NIN * IN_BYTES;   // 66,048 / 66,560 bytes per stage
+  static constexpr int GROUPS_IN = UNITS / 8;         // groups of 8 units per input
+};
+template <int KIND>
+struct NIn { static constexpr int v = (KIND == CTB_TR_EDD || KIND == CTB_TR_GDD) ? 2 : 1; };
 enum { F_SLOT = 1, F_FIRST = 2, F_LAST = 4, F_EXIT = 8 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -204,6 +218,7 @@ __device__ __forceinline__ double fold_quads(double a0, double a1, double a2, do
 template <typename TIN, int KIND, int NOUT, bool CHECK>
 __device__ __forceinline__ void reduce_region(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
                                               int lane, double (&v)[NOUT]) {
+  constexpr int CTB_ROWB = Geo<1>::ROWB;
   double acc[4][NOUT];
 #pragma unroll
   for (int g = 0; g < 4; ++g)
@@ -238,6 +253,7 @@ __device__ __forceinline__ void reduce_region(const CtbTr& tr, uint32_t tile_a, 
 template <int KIND, int NOUT>
 __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
                                                     int lane, double (&v)[NOUT]) {
+  constexpr int CTB_ROWB = Geo<1>::ROWB;
   double acc[4][NOUT];
 #pragma unroll
   for (int g = 0; g < 4; ++g)
@@ -280,8 +296,46 @@ __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t ti
   return __all_sync(0xffffffffu, ok);
 }
 
+// Two-input transforms (Snyder EDD / GDD from tasmin, tasmax): the same quad loop, the lane's entry
+// evaluated on its four days.  fp64 ALU bound; NaN results are skipped by a select (the reference's
+// skipna sum), and the zero-weight padding of the last quad never meets a value (0 * inf).
+template <typename TIN, int KIND, int NOUT>
+__device__ __forceinline__ void reduce_region2(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
+                                               int lane, double (&v)[NOUT]) {
+  constexpr int ROWB = Geo<2>::ROWB, IN_BYTES = Geo<2>::IN_BYTES;
+  double acc[4][NOUT];
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) acc[g][j] = 0.0;
+  for (int q = 0; q < nq; ++q, ent_a += 4 * (uint32_t)sizeof(CtbEnt)) {
+    const uint4 m = lds_u4(ent_a);
+    const double w = __hiloint2double((int)m.y, (int)m.x);
+    const bool wnz = w != 0.0;
+    const uint32_t xa = tile_a + m.z;
+    TIN lo[4], hi[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      lo[g] = lds_val<TIN>(xa + g * 8 * ROWB);
+      hi[g] = lds_val<TIN>(xa + IN_BYTES + g * 8 * ROWB);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double f[NOUT];
+      ctb_apply<KIND, NOUT>(tr, (double)lo[g], (double)hi[g], f);
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) acc[g][j] = fma(w, (wnz && f[j] == f[j]) ? f[j] : 0.0, acc[g][j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NOUT; ++j) v[j] = fold_quads(acc[0][j], acc[1][j], acc[2][j], acc[3][j], lane);
+}
+
 template <typename TIN, int KIND, int NOUT, int THREADS, int S, bool GROUPS>
 __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a) {
+  constexpr int NIN = NIn<KIND>::v;
+  using G = Geo<NIN>;
+  constexpr int CTB_ROWB = G::ROWB, CTB_STREAM_TILE_BYTES = G::TILE_BYTES;
   constexpr int NWARP = THREADS / 32;
   constexpr int NCW = NWARP - NP;   // consumer warps 0 .. NCW-1; the producers are the LAST warps:
                                     // the issue arbiter prefers high warp ids, and a copy that is
@@ -321,8 +375,21 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
     const int pw = warp - NCW;
     const bool leader = (pw == 0 && lane == 0);
     const int l8 = lane & 7, l4 = lane >> 3;
-    const TIN* const X = reinterpret_cast<const TIN*>(a.x0);
+    const TIN* const X0 = reinterpret_cast<const TIN*>(a.x0);
+    const TIN* const X1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) : X0;
     const int64_t row_step = 4 * a.stride;
+    // this lane's unit groups: group G = pw + NP * gi of the stage's 16 (input G / GROUPS_IN, units
+    // (G % GROUPS_IN) * 8 + l8 of that input); dst_of[gi]: byte offset inside the stage's row 0
+    int unit_of[UPW];
+    uint32_t dst_of[UPW];
+    bool second[UPW];
+#pragma unroll
+    for (int gi = 0; gi < UPW; ++gi) {
+      const int Gi = pw + NP * gi;
+      second[gi] = NIN == 2 && Gi >= G::GROUPS_IN;
+      unit_of[gi] = (Gi % G::GROUPS_IN) * 8 + l8;
+      dst_of[gi] = (uint32_t)((second[gi] ? G::IN_BYTES : 0) + unit_of[gi] * 16);
+    }
     int offN[UPW];
     int4 dN = make_int4(0, 0, 0, 0);
     auto prefetch_unit = [&](int unit) {   // descriptor + this lane's unit offsets, one unit ahead
@@ -332,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
 #pragma unroll
         for (int gi = 0; gi < UPW; ++gi)
           if (pw + NP * gi < NG)
-            offN[gi] = __ldg(a.unit_tab + (size_t)b * CTB_TILE_UNITS + (pw + NP * gi) * 8 + l8);
+            offN[gi] = __ldg(a.unit_tab + (size_t)b * CTB_TILE_UNITS + unit_of[gi]);
       }
     };
     // Work units: the first one is the CTA's own, the others come from a device counter, fetched by
@@ -363,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
       }
       bool ok[UPW];   // this lane's 16-byte units of the bundle (at most 128 per day and input)
 #pragma unroll
-      for (int gi = 0; gi < UPW; ++gi) ok[gi] = (pw + NP * gi) * 8 + l8 < d.w;
+      for (int gi = 0; gi < UPW; ++gi) ok[gi] = pw + NP * gi < NG && unit_of[gi] < d.w;
       const int tb_begin = (unit / a.n_bundles) * a.chunk_tb;
       const int tb_end = min(tb_begin + a.chunk_tb, a.n_tb);
       for (int tb = tb_begin; tb < tb_end; ++tb) {
@@ -377,16 +444,16 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
 #endif
         {
           // one 64-bit multiply-add per copy: the row pointer advances by 4 day planes per step
-          uint32_t dst = tiles_a + (uint32_t)stage * CTB_STREAM_TILE_BYTES + (uint32_t)((pw * 8 + l8) * 16 + l4 * CTB_ROWB);
+          uint32_t dst = tiles_a + (uint32_t)stage * CTB_STREAM_TILE_BYTES + (uint32_t)(l4 * CTB_ROWB);
           const int n_days = min(CTB_TB, a.T - tb * CTB_TB);
           if (a.tix == nullptr) {
-            const TIN* row = X + (int64_t)(tb * CTB_TB + l4) * a.stride;
+            int64_t ro = (int64_t)(tb * CTB_TB + l4) * a.stride;
 #pragma unroll
-            for (int dd = 0; dd < CTB_TB / 4; ++dd, dst += 4 * CTB_ROWB, row += row_step) {
+            for (int dd = 0; dd < CTB_TB / 4; ++dd, dst += 4 * CTB_ROWB, ro += row_step) {
               if (dd * 4 + l4 < n_days) {
 #pragma unroll
                 for (int gi = 0; gi < UPW; ++gi)
-                  if (ok[gi]) cp_async16(dst + gi * NP * 128, row + off[gi]);
+                  if (ok[gi]) cp_async16(dst + dst_of[gi], (second[gi] ? X1 : X0) + ro + off[gi]);
               }
 #if CTB_PACE_NS > 0
               __nanosleep(CTB_PACE_NS);
@@ -396,10 +463,10 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
 #pragma unroll 2
             for (int dd = 0; dd < CTB_TB / 4; ++dd, dst += 4 * CTB_ROWB) {
               if (dd * 4 + l4 < n_days) {
-                const TIN* row = X + (int64_t)__ldg(a.tix + tb * CTB_TB + dd * 4 + l4) * a.stride;
+                const int64_t ro = (int64_t)__ldg(a.tix + tb * CTB_TB + dd * 4 + l4) * a.stride;
 #pragma unroll
                 for (int gi = 0; gi < UPW; ++gi)
-                  if (ok[gi]) cp_async16(dst + gi * NP * 128, row + off[gi]);
+                  if (ok[gi]) cp_async16(dst + dst_of[gi], (second[gi] ? X1 : X0) + ro + off[gi]);
               }
             }
           }
@@ -465,8 +532,13 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
         const uint32_t ea = ent_a + (sg.y & 0xffffu) * 4u * (uint32_t)sizeof(CtbEnt);
         double v[NOUT];
         bool done = false;
-        if constexpr (sizeof(TIN) == 4) done = reduce_region_widen<KIND, NOUT>(a.tr, tile_a, ea, nq, lane, v);
-        if (!done) {
+        if constexpr (NIN == 2) {
+          reduce_region2<TIN, KIND, NOUT>(a.tr, tile_a, ea, nq, lane, v);
+          done = true;
+        } else if constexpr (sizeof(TIN) == 4) {
+          done = reduce_region_widen<KIND, NOUT>(a.tr, tile_a, ea, nq, lane, v);
+        }
+        if constexpr (NIN == 1) if (!done) {
           reduce_region<TIN, KIND, NOUT, false>(a.tr, tile_a, ea, nq, lane, v);
           bool bad = false;
 #pragma unroll
@@ -506,9 +578,11 @@ template <typename TIN, int KIND, int NOUT>
 int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   // 32 warps of 64 registers; the multi-output polynomials keep 4 fp64 accumulators per output and
   // lane and take 24 warps of 80 registers instead of spilling
-  constexpr int THREADS = (KIND == CTB_TR_POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
+  // ... and the Snyder forms 16 warps of 128 registers (fp64 ALU bound: registers buy more than warps)
+  constexpr int NIN = NIn<KIND>::v;
+  constexpr int THREADS = NIN == 2 ? (NOUT <= 2 ? 640 : 512) : (KIND == CTB_TR_POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
   constexpr int S = CTB_STAGES;   // tile stages: one being reduced, up to two landing
-  constexpr size_t SMEM = (size_t)S * CTB_STREAM_TILE_BYTES + 2 * CTB_META_CAP;
+  constexpr size_t SMEM = (size_t)S * Geo<NIN>::TILE_BYTES + 2 * CTB_META_CAP;
   static_assert(SMEM <= 227 * 1024 - 512, "shared memory budget");
   static int n_sm[64] = {0};
   static bool attr_set[64][2] = {{false}};
@@ -522,7 +596,7 @@ int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
     attr_set[dev][groups] = true;
   }
   a.n_stages = S;
-  a.tile_stride = CTB_STREAM_TILE_BYTES;
+  a.tile_stride = Geo<NIN>::TILE_BYTES;
   a.n_tb = (a.T + CTB_TB - 1) / CTB_TB;
   // units: chunks of up to 8 time blocks, shorter when there would be too few units to fill the GPU
   const int64_t tiles = (int64_t)P->n_bundles * a.n_tb;
@@ -539,8 +613,7 @@ int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   a.n_items = (int)n_units;
   // {next unit, CTAs done} pairs, zero between launches (the kernel re-arms its pair); launches of
   // one plan that run concurrently on different streams take different pairs
-  a.work_counter = P->d_work_counter + CTB_N_WORK_COUNTERS +
-                   2 * (P->work_counter_slot.fetch_add(1) % (CTB_N_WORK_COUNTERS / 2));
+  a.work_counter = P->d_work_counter + 2 * (P->work_counter_slot.fetch_add(1) % (CTB_N_WORK_COUNTERS / 2));
   if (n_units > 0) {
     const unsigned grid = (unsigned)std::min<int64_t>(n_units, n_sm[dev]);
     k<<<grid, THREADS, SMEM, st>>>(a);
@@ -552,14 +625,17 @@ int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
 template <typename TIN>
 int launch_kind(const ctb_plan* P, const AggArgs& a, int kind, int n_out, cudaStream_t st) {
   if (kind == CTB_TR_IDENTITY) return launch<TIN, CTB_TR_IDENTITY, 1>(P, a, st);
-  if (kind == CTB_TR_POLY) {
-    switch (n_out) {
-      case 1: return launch<TIN, CTB_TR_POLY, 1>(P, a, st);
-      case 2: return launch<TIN, CTB_TR_POLY, 2>(P, a, st);
-      case 3: return launch<TIN, CTB_TR_POLY, 3>(P, a, st);
-      case 4: return launch<TIN, CTB_TR_POLY, 4>(P, a, st);
-    }
+#define CTB_NOUT_SWITCH(K)                                   \
+  switch (n_out) {                                           \
+    case 1: return launch<TIN, K, 1>(P, a, st);              \
+    case 2: return launch<TIN, K, 2>(P, a, st);              \
+    case 3: return launch<TIN, K, 3>(P, a, st);              \
+    case 4: return launch<TIN, K, 4>(P, a, st);              \
   }
+  if (kind == CTB_TR_POLY) { CTB_NOUT_SWITCH(CTB_TR_POLY) }
+  if (kind == CTB_TR_EDD) { CTB_NOUT_SWITCH(CTB_TR_EDD) }
+  if (kind == CTB_TR_GDD) { CTB_NOUT_SWITCH(CTB_TR_GDD) }
+#undef CTB_NOUT_SWITCH
   ctb_set_error("streaming kernel: transform=%d n_out=%d unsupported", kind, n_out);
   return CTB_ERR_INVALID;
 }

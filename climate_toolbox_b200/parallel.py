@@ -85,60 +85,77 @@ def all_gather_time(local, T, group=None, align=32):
     return full.reshape(lead + (T,))
 
 
+class _ShardBuffers:
+    """Streams and buffers of :func:`aggregate_shard_overlapped`, allocated once per (plan, T, n_out,
+    pieces, world): a collective must not wait for ``cudaMalloc``, and blocks that are used on a side
+    stream do not come back to the caching allocator quickly."""
+
+    def __init__(self, plan, T, n_out, pieces, world, rank, gather):
+        dev = plan.device
+        self.sizes = shard_sizes(T, world)
+        self.col0 = [sum(self.sizes[:r]) for r in range(world)]
+        self.t0, self.tl = self.col0[rank], self.sizes[rank]
+        tmax = max(self.sizes)
+        tiles = (tmax + 31) // 32
+        pieces = max(1, min(pieces, tiles))
+        # piece boundaries inside a shard: the same on every rank (relative to the largest shard), 32-aligned
+        self.cuts = [min(tmax, ((tiles * k) // pieces) * 32) for k in range(pieces)] + [tmax]
+        self.M = n_out * plan.R
+        self.loc = [torch.empty((n_out, plan.R, self.cuts[k + 1] - self.cuts[k]), dtype=torch.float64, device=dev)
+                    for k in range(pieces)]
+        self.recv = [torch.empty((world * self.M, self.cuts[k + 1] - self.cuts[k]), dtype=torch.float64, device=dev)
+                     for k in range(pieces)] if gather else None
+        self.out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev) if gather else None
+        self.side = torch.cuda.Stream(dev) if gather else None
+
+
 def aggregate_shard_overlapped(plan, x0, x1, stride, T, kind="identity", params=(), n_out=1, group=None,
                                pieces=4, gather=True, out=None):
     """Time-sharded aggregation of device-resident TIME_MAJOR inputs with the output gather
     overlapped: this rank aggregates days ``shard_range(T)`` of ``x0`` (``[T, stride]``, every rank
     holds or views the same time axis) in ``pieces`` pieces; the ``all_gather`` of piece k runs on
     a side stream while the kernel of piece k+1 runs, and lands through one strided copy in the
-    final ``[n_out, R, T]`` layout.  Returns ``(out, info)``; with ``gather=False`` only the local
-    block ``[n_out, R, T_local]``."""
+    final ``[n_out, R, T]`` layout.  Returns ``(out, info)``; with ``gather=False`` only the list of
+    local piece blocks.  Buffers live with the plan and are reused by the next call of the same shape
+    (the returned ``out`` is overwritten then)."""
     from . import _engine as E
     from . import _native as N
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = plan.device
-    sizes = shard_sizes(T, world)
-    col0 = [sum(sizes[:r]) for r in range(world)]
-    t0, tl = col0[rank], sizes[rank]
-    tmax = max(sizes)
-    # piece boundaries inside a shard: the same on every rank (relative to the largest shard), 32-aligned
-    tiles = (tmax + 31) // 32
-    pieces = max(1, min(pieces, tiles))
-    cuts = [min(tmax, ((tiles * k) // pieces) * 32) for k in range(pieces)] + [tmax]
-    R, M = plan.R, n_out * plan.R
+    cache = plan.__dict__.setdefault("_shard_buffers", {})
+    key = (T, n_out, pieces, world, rank, bool(gather))
+    if key not in cache:
+        if len(cache) > 4:
+            cache.clear()
+        cache[key] = _ShardBuffers(plan, T, n_out, pieces, world, rank, gather)
+    sb = cache[key]
     if gather and out is None:
-        out = torch.empty((n_out, R, T), dtype=torch.float64, device=dev)
+        out = sb.out
     main = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(dev) if gather else None
-    locs, done = [], []
-    for k in range(pieces):
-        c0, c1 = cuts[k], cuts[k + 1]
-        n = max(0, min(c1, tl) - c0)           # this rank's valid days in the piece
-        loc = torch.empty((n_out, R, c1 - c0), dtype=torch.float64, device=dev)
+    if gather:
+        sb.side.wait_stream(main)      # the previous call's consumers of `out` / `recv` are ordered before us
+    for k in range(len(sb.loc)):
+        c0, c1 = sb.cuts[k], sb.cuts[k + 1]
+        n = max(0, min(c1, sb.tl) - c0)           # this rank's valid days in the piece
+        loc = sb.loc[k]
         if n > 0:
-            a = x0[t0 + c0: t0 + c0 + n]
-            b = x1[t0 + c0: t0 + c0 + n] if x1 is not None else None
+            a = x0[sb.t0 + c0: sb.t0 + c0 + n]
+            b = x1[sb.t0 + c0: sb.t0 + c0 + n] if x1 is not None else None
             E.aggregate_device(plan, a, b, N.LAYOUT_TIME_MAJOR, stride, None, n, kind, params, n_out,
                                out=loc, out_ld=c1 - c0)
-        locs.append(loc)
         if gather:
             ev = torch.cuda.Event()
             ev.record(main)
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                recv = torch.empty((world * M, c1 - c0), dtype=torch.float64, device=dev)
-                dist.all_gather_into_tensor(recv, loc.view(M, c1 - c0), group=group)
-                _scatter_columns(out.view(M, T), recv.view(world, M, c1 - c0),
-                                 [max(0, min(c1, s) - c0) for s in sizes], col0, c0)
-                recv.record_stream(side)
-                loc.record_stream(side)
-            done.append(side)
+            sb.side.wait_event(ev)
+            with torch.cuda.stream(sb.side):
+                dist.all_gather_into_tensor(sb.recv[k], loc.view(sb.M, c1 - c0), group=group)
+                _scatter_columns(out.view(sb.M, T), sb.recv[k].view(world, sb.M, c1 - c0),
+                                 [max(0, min(c1, s) - c0) for s in sb.sizes], sb.col0, c0)
     if not gather:
-        return torch.cat([l[:, :, : max(0, min(cuts[k + 1], tl) - cuts[k])] for k, l in enumerate(locs)], dim=2), \
-            {"t0": t0, "t1": t0 + tl}
-    main.wait_stream(side)
-    return out, {"t0": t0, "t1": t0 + tl, "pieces": pieces,
-                 "bytes_received": int(8 * M * (T - tl))}
+        return sb.loc, {"t0": sb.t0, "t1": sb.t0 + sb.tl, "cuts": sb.cuts}
+    main.wait_stream(sb.side)
+    return out, {"t0": sb.t0, "t1": sb.t0 + sb.tl, "pieces": len(sb.loc),
+                 "bytes_received": int(8 * sb.M * (T - sb.tl))}
 
 
 def aggregate_time_sharded(ds, variable, aggwt, agglev, weights, backup_aggwt="areawt", gather=True,

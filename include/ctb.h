@@ -151,8 +151,8 @@ int ctb_plan_row_weights(const ctb_plan* plan, double* w_out /*[n_rows]*/);
  *                  A time-chunked caller passes out + t0 with out_ld = total T.
  *  workspace     : DEVICE scratch of ctb_aggregate_workspace_bytes() bytes (may be
  *                  NULL when that is 0)
- *  variant       : 0 = auto; 1 = staged (TIME_MAJOR only: the streaming kernel for IDENTITY /
- *                  POLY, the Snyder kernel for EDD / GDD); 2 = direct warp-per-region kernel.  | 0x100: x0/x1 are MAPPED PINNED HOST memory read
+ *  variant       : 0 = auto; 1 = the streaming kernel (TIME_MAJOR inputs with 16-byte aligned planes;
+ *                  others fall back to 2); 2 = direct warp-per-region kernel.  | 0x100: x0/x1 are MAPPED PINNED HOST memory read
  *                  in place over PCIe (zero-copy: only the referenced gridcells cross the bus)
  */
 size_t ctb_aggregate_workspace_bytes(const ctb_plan* plan, int64_t T, int n_out);
