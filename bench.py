@@ -337,9 +337,25 @@ class Bench:
         xs = self.inputs(workload, T, variant=variant)
         ncell = len(lat) * len(lon)
         t_plan = time.perf_counter()
-        plan = E.get_plan(E.GridSpec(lat, lon), df, aggwt, "hierid", stage_bytes=4 * n_in, device=self.dev)
+        plan = E.get_plan(E.GridSpec(lat, lon), df, aggwt, "hierid", stage_bytes=4 * n_in, device=self.dev,
+                          compact=(variant == "packed"))
         torch.cuda.synchronize()
         plan_ms = (time.perf_counter() - t_plan) * 1e3
+        pack_ms = None
+        if variant == "packed":
+            # device-side compaction of the archive into packed planes [T][n_packed_cells] (only the
+            # referenced 16-byte pieces, runs aligned to 64 bytes): paid once, reused by every later
+            # aggregation of the same footprint (other weights, poly orders, ensemble members)
+            import ctypes as C
+            width = plan.info["n_packed_cells"]
+            packed = torch.empty((T, width), dtype=torch.float32, device=self.dev)
+
+            def pack():
+                N.check(N.lib().ctb_pull_pack(plan._h, C.c_void_p(xs[0].data_ptr()), N.F32, ncell, None, 0, T,
+                                              C.c_void_p(packed.data_ptr()), E._stream_ptr(self.dev)))
+            _, pack_ms, _ = self.timed(pack, 5, 3)
+            xs = [packed]
+            ncell = width
         groups = None
         n_cols = T
         if groups_period:
@@ -367,7 +383,7 @@ class Bench:
         ms_step, kern_ms, launches = self.timed(step, steps, warmup)
         if streaming:
             kern_ms = ms_step / years
-        res = {"plan": plan, "xs": xs, "out": out, "T": T, "ms_per_step": ms_step, "kern_ms": kern_ms,
+        res = {"plan": plan, "xs": xs, "out": out, "T": T, "ms_per_step": ms_step, "kern_ms": kern_ms, "pack_ms": pack_ms,
                "launches": launches, "years": years, "plan_ms": plan_ms,
                "value": self.world * plan.R * T * years / (ms_step * 1e-3),
                "checksum": float(torch.nansum(out).item())}
@@ -546,7 +562,8 @@ def run_ours(args):
         head["xs"] = None
         torch.cuda.empty_cache()
         st = max(5, min(args.steps, 10))
-        for name, wl, kw in (("config2_bcsd_like", "config2", {"variant": "bcsd_like"}),
+        for name, wl, kw in (("config2_packed_planes", "config2", {"variant": "packed"}),
+                             ("config2_bcsd_like", "config2", {"variant": "bcsd_like"}),
                              ("config2_nan_2pct_of_land", "config2", {"variant": "nan2pct"}),
                              ("config2_annual_sums", "config2", {"groups_period": 365}),
                              ("config3", "config3", {}), ("config4", "config4", {}),
@@ -559,6 +576,10 @@ def run_ours(args):
                          "full_job_seconds_extrapolated": ENSEMBLE_YEARS / r["years"] * r["ms_per_step"] * 1e-3}
             if name == "config2_annual_sums":
                 extra = {"note": "fused time reduction: output [R][4 years] instead of [R][1460 days]"}
+            if name == "config2_packed_planes":
+                extra = {"pack_ms_one_shot": r["pack_ms"], "one_shot_total_ms": r["pack_ms"] + r["kern_ms"],
+                         "note": "archive compacted on the device (ctb_pull_pack on a device source) into packed planes; "
+                                 "ms_per_launch is the amortised cost of every aggregation after the first"}
             also[name] = B.summary(wl, r, traffic_all.get(name), extra)
             del r
             torch.cuda.empty_cache()

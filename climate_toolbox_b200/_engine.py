@@ -179,8 +179,15 @@ def region_codes(labels):
 
 
 def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4, device=None,
-             smem_budget=0, cache=True, compact=False, elem_bytes=4, trusted=False):
-    """Build (or fetch) the device plan for (grid, weights[lat, lon, agglev, aggwt, backup])."""
+             smem_budget=0, cache=True, compact=False, elem_bytes=4, trusted=False, cell_gate=None):
+    """Build (or fetch) the device plan for (grid, weights[lat, lon, agglev, aggwt, backup]).
+    ``cell_gate``: uint32 per PHYSICAL gridcell (growing-season gate, ``_native.gate_word``) or None."""
+    if cell_gate is not None:
+        cell_gate = np.ascontiguousarray(cell_gate, dtype=np.uint32).reshape(-1)
+        if cell_gate.size != grid.nlat_phys * grid.nlon_phys:
+            raise ValueError("cell_gate has {} entries for {} gridcells".format(
+                cell_gate.size, grid.nlat_phys * grid.nlon_phys))
+    gate_fp = None if cell_gate is None else _buf_fp(cell_gate.view(np.uint8))
     device = device or default_device()
     for col in ("lat", "lon", agglev, aggwt, backup_aggwt):
         if col not in weights:
@@ -195,7 +202,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
         grid.digest(gh)
         with np.errstate(all="ignore"):
             fp = (id(weights), len(weights), aggwt, agglev, backup_aggwt, stage_bytes, smem_budget,
-                  bool(compact), int(elem_bytes), str(device), gh.hexdigest(),
+                  bool(compact), int(elem_bytes), str(device), gh.hexdigest(), gate_fp,
                   # `trusted`: a private frame of the caller (never edited in place): identity is enough
                   () if trusted else tuple(_col_fp(weights[c].values)
                                            for c in ("lat", "lon", aggwt, backup_aggwt, agglev)))
@@ -215,6 +222,8 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     for a in (row_lat, row_lon, wp, wb, codes):
         h.update(a.tobytes())
     h.update(repr((stage_bytes, smem_budget, bool(compact), int(elem_bytes), str(device), len(labels))).encode())
+    if cell_gate is not None:
+        h.update(cell_gate.tobytes())
     key = h.hexdigest()
     if cache and key in _PLAN_CACHE:
         _PLAN_CACHE.move_to_end(key)
@@ -226,6 +235,7 @@ def get_plan(grid, weights, aggwt, agglev, backup_aggwt="areawt", stage_bytes=4,
     opts.smem_budget_bytes = int(smem_budget)
     opts.compact = 1 if compact else 0
     opts.elem_bytes = int(elem_bytes)
+    opts.cell_gate = cell_gate.ctypes.data if cell_gate is not None else None
     handle = C.c_void_p()
     bad_row, bad_axis = C.c_int64(-1), C.c_int32(-1)
     rc = N.lib().ctb_plan_build(
@@ -311,9 +321,10 @@ def _workspace(plan, T, n_out, layout, variant, groups, workspace):
 
 
 def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out, variant, out, out_ld,
-            workspace, stream, groups=None, t_begin=0, flush=True):
-    """Raw-pointer call of ctb_aggregate / ctb_aggregate_grouped (p0/p1: device or mapped-host
-    addresses).  With ``groups`` the result is [n_out, R, n_groups]."""
+            workspace, stream, groups=None, t_begin=0, flush=True, doy=None):
+    """Raw-pointer call of ctb_aggregate_ex (p0/p1: device or mapped-host addresses).  With ``groups``
+    the result is [n_out, R, n_groups]; ``doy`` (int array, day of year of every day of the time axis)
+    switches the growing-season gate of a plan built with ``cell_gate`` on."""
     dev = plan.device
     L = N.lib()
     if out is None:
@@ -321,25 +332,26 @@ def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out
                           device=dev)
     workspace = _workspace(plan, T, n_out, layout, variant, groups, workspace)
     tix_d = plan.time_index_device(tix)
+    doy_d = plan.time_index_device(doy)
     pa, pp = _params_array(kind, params)
-    head = (plan._h, C.c_void_p(p0), C.c_void_p(p1) if p1 else None, ctb_dtype, layout, int(stride),
-            C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
-            _KIND[kind], pp, int(pa.size), int(n_out))
-    tail = (C.c_void_p(out.data_ptr()), int(out_ld),
-            C.c_void_p(workspace.data_ptr()) if workspace is not None else None,
-            int(workspace.numel() * 8) if workspace is not None else 0, int(variant),
-            _stream_ptr(dev, stream))
-    if groups is None:
-        rc = L.ctb_aggregate(*head, *tail)
-    else:
-        rc = L.ctb_aggregate_grouped(*head, groups._h, int(t_begin), 1 if flush else 0, *tail)
+    o = N.AggOpts()
+    o.groups = groups._h if groups is not None else None
+    o.t_begin, o.flush = int(t_begin), 1 if flush else 0
+    o.day_of_year = doy_d.data_ptr() if doy_d is not None else None
+    rc = L.ctb_aggregate_ex(
+        plan._h, C.c_void_p(p0), C.c_void_p(p1) if p1 else None, ctb_dtype, layout, int(stride),
+        C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
+        _KIND[kind], pp, int(pa.size), int(n_out), C.byref(o), C.c_void_p(out.data_ptr()), int(out_ld),
+        C.c_void_p(workspace.data_ptr()) if workspace is not None else None,
+        int(workspace.numel() * 8) if workspace is not None else 0, int(variant),
+        _stream_ptr(dev, stream))
     N.check(rc)
     return out
 
 
 def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", params=(), n_out=1,
                      variant=N.VARIANT_AUTO, out=None, out_ld=0, stream=None, workspace=None, groups=None,
-                     t_begin=0, flush=True):
+                     t_begin=0, flush=True, doy=None):
     """Launch the fused kernel on device-resident inputs.
 
     ``x0`` / ``x1``: contiguous CUDA tensors (f32/f64).  ``tix``: numpy int array of
@@ -355,7 +367,7 @@ def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", para
         raise ValueError("the two inputs must agree in dtype and shape")
     return _launch(plan, x0.data_ptr(), x1.data_ptr() if x1 is not None else 0, _T2CTB[x0.dtype], layout,
                    stride, tix, T, kind, params, n_out, variant, out, out_ld, workspace, stream, groups,
-                   t_begin, flush)
+                   t_begin, flush, doy)
 
 
 def _all_pinned(xs):
@@ -454,7 +466,7 @@ def pack_threads():
 
 
 def _aggregate_pull(plan, xs, stride, tix, T, kind, params, n_out, variant, groups, out, host_out=None,
-                    chunk_bytes=4 << 30):
+                    chunk_bytes=4 << 30, doy=None):
     """Pinned host arrays + compact plan: the GPU packs for itself (``ctb_pull_pack`` reads the
     referenced pieces over PCIe into a packed device buffer), then the kernel aggregates the packed
     planes.  No host core touches the data; pulls and kernels queue on one stream.  With ``host_out``
@@ -485,7 +497,8 @@ def _aggregate_pull(plan, xs, stride, tix, T, kind, params, n_out, variant, grou
         TRANSFER_BYTES["h2d"] += len(xs) * n * plan.info["n_pieces_distinct"] * 4 * itemsize
         if groups is None:
             aggregate_device(plan, bufs[0], bufs[1] if len(bufs) > 1 else None, N.LAYOUT_TIME_MAJOR, width, None,
-                             n, kind, params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
+                             n, kind, params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws,
+                             doy=None if doy is None else doy[t0: t0 + n])
             if back is not None:
                 ev = torch.cuda.Event()
                 ev.record(main)
@@ -497,7 +510,7 @@ def _aggregate_pull(plan, xs, stride, tix, T, kind, params, n_out, variant, grou
         else:
             aggregate_device(plan, bufs[0], bufs[1] if len(bufs) > 1 else None, N.LAYOUT_TIME_MAJOR, width, None,
                              n, kind, params, n_out, variant, out=out, workspace=ws, groups=groups, t_begin=t0,
-                             flush=(t0 == starts[-1]))
+                             flush=(t0 == starts[-1]), doy=doy)
     if back is not None:
         out.record_stream(back)
         main.wait_stream(back)
@@ -507,7 +520,7 @@ def _aggregate_pull(plan, xs, stride, tix, T, kind, params, n_out, variant, grou
 
 def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(), n_out=1,
                    variant=N.VARIANT_AUTO, chunk_bytes=192 << 20, zero_copy=None, threads=0, groups=None,
-                   ingest=None, host_out=None):
+                   ingest=None, host_out=None, doy=None):
     """Host (numpy) inputs -> CUDA tensor [n_out, R, T] (with ``groups``: [n_out, R, n_groups]).
 
     ``xs``: list of 1 or 2 C-contiguous numpy arrays viewed as 2-D
@@ -535,7 +548,7 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
         d = [torch.from_numpy(x).to(dev, non_blocking=True) for x in xs]
         TRANSFER_BYTES["h2d"] += sum(x.nbytes for x in xs)
         return aggregate_device(plan, d[0], d[1] if len(d) > 1 else None, layout, stride, tix, T,
-                                kind, params, n_out, variant, out=out, groups=groups)
+                                kind, params, n_out, variant, out=out, groups=groups, doy=doy)
     if zero_copy is None:
         # opt-in: on the round-1 box the in-place read moved 2.5 GB at ~7 GB/s (16-byte requests
         # over PCIe) and lost to copying all 6 GB at ~21 GB/s (profiles/r1_e2e_notes.md)
@@ -546,7 +559,7 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
         # referenced gridcells (~30 % of a global land/ocean grid) cross the bus
         return _launch(plan, xs[0].ctypes.data, xs[1].ctypes.data if len(xs) > 1 else 0,
                        _NP2CTB[xs[0].dtype], layout, stride, tix, T, kind, params, n_out,
-                       N.VARIANT_STAGED | 0x100, out, 0, None, None, groups)
+                       N.VARIANT_STAGED | 0x100, out, 0, None, None, groups, 0, True, doy)
 
     if ingest is None:
         ingest = os.environ.get("CTB_INGEST", "auto")
@@ -555,7 +568,7 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
             all(x.ctypes.data % 16 == 0 for x in xs) and _all_pinned(xs):
         # pinned (device-accessible) source: the GPU pulls the referenced pieces itself
         out, filled = _aggregate_pull(plan, xs, stride, tix, T, kind, params, n_out, variant, groups, out,
-                                      host_out[0] if host_out is not None else None)
+                                      host_out[0] if host_out is not None else None, doy=doy)
         if host_out is not None:
             host_out[1] = filled
         return out
@@ -623,11 +636,12 @@ def aggregate_host(plan, xs, layout, stride, tix, T, kind="identity", params=(),
             main.wait_event(ready)
             if groups is None:
                 aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, width, rel, n, kind,
-                                 params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws)
+                                 params, n_out, variant, out=_OffsetOut(out, t0), out_ld=T, workspace=ws,
+                                 doy=None if doy is None else doy[t0: t1])
             else:
                 aggregate_device(plan, cur[0], cur[1] if len(cur) > 1 else None, layout, width, rel, n, kind,
                                  params, n_out, variant, out=out, workspace=ws, groups=groups, t_begin=t0,
-                                 flush=(t0 == starts[-1]))
+                                 flush=(t0 == starts[-1]), doy=doy)
             ev = torch.cuda.Event()
             ev.record(main)
             free_ev[slot] = ev

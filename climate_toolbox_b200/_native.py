@@ -25,13 +25,28 @@ SYMBOLS = (
     "ctb_plan_get_info", "ctb_plan_row_cells", "ctb_plan_den", "ctb_plan_row_weights",
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
     "ctb_host_pack", "ctb_pull_pack", "ctb_copy_rows_to_host", "ctb_time_groups_create", "ctb_time_groups_free", "ctb_time_groups_count",
-    "ctb_aggregate_grouped_workspace_bytes", "ctb_aggregate_grouped",
+    "ctb_aggregate_grouped_workspace_bytes", "ctb_aggregate_grouped", "ctb_aggregate_ex",
 )
 
 
 class PlanOpts(C.Structure):
     _fields_ = [("stage_bytes_per_cell_day", C.c_int32), ("smem_budget_bytes", C.c_int32),
-                ("compact", C.c_int32), ("elem_bytes", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("compact", C.c_int32), ("elem_bytes", C.c_int32), ("reserved", C.c_int32 * 4),
+                ("cell_gate", C.c_void_p)]
+
+
+class AggOpts(C.Structure):
+    _fields_ = [("groups", C.c_void_p), ("t_begin", C.c_int64), ("flush", C.c_int32), ("reserved", C.c_int32),
+                ("day_of_year", C.c_void_p)]
+
+
+GATE_ALWAYS = 511 << 9
+GATE_NEVER = 511          # empty interval, no wrap
+
+
+def gate_word(first, last, wrap):
+    """first_day | last_day << 9 | wrap << 18 (include/ctb.h, ctb_plan_opts.cell_gate)."""
+    return int(first) | (int(last) << 9) | (int(bool(wrap)) << 18)
 
 
 class PlanInfo(C.Structure):
@@ -84,6 +99,9 @@ def lib():
     L.ctb_aggregate.restype = C.c_int
     L.ctb_aggregate.argtypes = [p, vp, vp, C.c_int, C.c_int, i64, vp, i64, C.c_int, dp, C.c_int,
                                 C.c_int, vp, i64, vp, C.c_size_t, C.c_int, vp]
+    L.ctb_aggregate_ex.restype = C.c_int
+    L.ctb_aggregate_ex.argtypes = [p, vp, vp, C.c_int, C.c_int, i64, vp, i64, C.c_int, dp, C.c_int,
+                                   C.c_int, C.POINTER(AggOpts), vp, i64, vp, C.c_size_t, C.c_int, vp]
     L.ctb_transform.restype = C.c_int
     L.ctb_transform.argtypes = [vp, vp, C.c_int, i64, C.c_int, dp, C.c_int, C.c_int, vp, vp]
     L.ctb_gather_rows.restype = C.c_int

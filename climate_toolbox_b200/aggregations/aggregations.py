@@ -118,17 +118,41 @@ def _coord_labels(ds, name):
     return np.asarray(ds._coords[name].values, dtype=np.float64)
 
 
-def _run_group(plan, views, kind, params, n_out, variant, groups=None, ingest=None, host_out=None):
+def _run_group(plan, views, kind, params, n_out, variant, groups=None, ingest=None, host_out=None, doy=None):
     """One fused launch for `n_out` outputs sharing the same sources."""
     v0 = views[0]
     if v0.on_device:
         out = E.aggregate_device(plan, views[0].data2d, views[1].data2d if len(views) > 1 else None,
                                  v0.layout, v0.stride, v0.tix, v0.T, kind, params, n_out, variant,
-                                 groups=groups)
+                                 groups=groups, doy=doy)
     else:
         out = E.aggregate_host(plan, [v.data2d for v in views], v0.layout, v0.stride, v0.tix, v0.T,
-                               kind, params, n_out, variant, groups=groups, ingest=ingest, host_out=host_out)
+                               kind, params, n_out, variant, groups=groups, ingest=ingest, host_out=host_out,
+                               doy=doy)
     return out
+
+
+def _season_gate(mask, ds, lat, lon, view, time_dim):
+    """GrowingSeasonMask -> (gate word of every PHYSICAL gridcell, day of year of every logical step)."""
+    from ..utils.utils import _day_of_year, _match
+    words = mask.gate_words()
+    never = np.uint32(N.GATE_NEVER)
+    words = np.where(mask.missing, never, words)
+    ii = _match(np.asarray(mask.lat, dtype=np.float64), lat, "lat")       # data labels -> mask rows
+    jj = _match(np.asarray(mask.lon, dtype=np.float64), lon, "lon")
+    logical = words[np.ix_(ii, jj)]
+    pi = view.lat_phys if view.lat_phys is not None else np.arange(len(lat))
+    pj = view.lon_phys if view.lon_phys is not None else np.arange(len(lon))
+    phys = np.full((view.nlat_phys, view.nlon_phys), never, dtype=np.uint32)
+    phys[np.ix_(np.asarray(pi), np.asarray(pj))] = logical
+    if time_dim not in ds._coords:
+        raise KeyError(time_dim)
+    doy = _day_of_year(ds._coords[time_dim].values)
+    if len(doy) != view.T:
+        raise ValueError("time coordinate has {} steps, the variable {}".format(len(doy), view.T))
+    if len(mask.time) == view.T and not np.array_equal(_day_of_year(mask.time), doy):
+        raise ValueError("season_mask was built for another time axis")
+    return phys, doy.astype(np.int32)
 
 
 def _time_group_ids(ds, dim, n, spec):
@@ -193,7 +217,7 @@ def _group_requests(reqs):
 
 def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant=N.VARIANT_AUTO,
                     device=None, smem_budget=0, keep_on_device=False, pack_host=True, trusted_weights=False,
-                    time_groups=None, time_dim="time", ingest=None):
+                    time_groups=None, time_dim="time", ingest=None, season_mask=None):
     lat, lon = _coord_labels(ds, "lat"), _coord_labels(ds, "lon")
     reqs = []
     for name in variables:
@@ -214,10 +238,18 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
         # host-resident (time, lat, lon) inputs go through a compact plan: only the referenced
         # gridcells are packed on the host and cross PCIe
         compact = (not v0.on_device) and v0.layout == N.LAYOUT_TIME_MAJOR and pack_host
+        cell_gate = doy = None
+        if season_mask is not None:
+            # growing-season gate: per-gridcell (first, last, wrap) into the plan, day of
+            # year of every step into the launch -- the lat x lon x time mask is never built
+            if v0.other_dims != (time_dim,):
+                raise NotImplementedError("season_mask needs variables over ({}, lat, lon), got {}".format(
+                    time_dim, v0.out_dims_template))
+            cell_gate, doy = _season_gate(season_mask, ds, lat, lon, v0, time_dim)
         plan = E.get_plan(grid, weights, aggwt, agglev, backup_aggwt,
                           stage_bytes=len(views) * v0.elem_bytes, device=dev,
                           smem_budget=smem_budget, compact=compact, elem_bytes=v0.elem_bytes,
-                          trusted=trusted_weights)
+                          trusted=trusted_weights, cell_gate=cell_gate)
         n_out = len(g["names"])
         groups = glabels = None
         other_shape = v0.other_shape
@@ -235,7 +267,7 @@ def _aggregate_core(ds, variables, aggwt, agglev, weights, backup_aggwt, variant
         if not keep_on_device and not v0.on_device and groups is None and v0.T > 0 and plan.R > 0:
             host, res_np = E.pinned_result_like(torch.empty((n_out, plan.R, v0.T), dtype=torch.float64, device="meta"))
             host_fill = [host, False]
-        out = _run_group(plan, views, g["kind"], g["params"], n_out, variant, groups, ingest, host_fill)  # [n_out, R, T]
+        out = _run_group(plan, views, g["kind"], g["params"], n_out, variant, groups, ingest, host_fill, doy)  # [n_out, R, T]
         # reference dim order: agglev takes the place of the first of (lat, lon)
         tmpl = ds._vars[g["names"][0]].dims
         first = min(tmpl.index("lat"), tmpl.index("lon"))
@@ -428,6 +460,10 @@ def weighted_aggregate_grid_to_regions(ds, variable, aggwt, agglev, weights=None
         :func:`prepare_spatial_weights_data`) with columns lat, lon, agglev, aggwt
         and ``backup_aggwt``.  ``None`` raises ``TypeError`` exactly like the
         reference (``:118-119`` calls a one-argument function without arguments).
+    season_mask : extension (``engine_opts``), default None.  The object
+        ``utils.get_daily_growing_season_mask`` returns (reference ``utils.py:119-153``): gridcell-days
+        outside their growing season do not enter the weighted sum -- equal to aggregating
+        ``ds[variable] * mask``, with the gate applied inside the kernel.
     time_groups : extension (``engine_opts``), default None.  ``"year"``, a block length or one
         label per time step: the daily region values of every group are SUMMED inside the kernel
         (``EDD_P = sum_d EDD_d``, reference ``transformations.py:17-21``) and the result has one

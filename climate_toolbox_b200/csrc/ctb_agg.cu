@@ -21,13 +21,13 @@ struct NIn { static constexpr int v = (KIND == CTB_TR_EDD || KIND == CTB_TR_GDD)
 
 // one CSR entry: acc_j += w * f_j(x), NaN products skipped (skipna sum, aggregations.py:78)
 template <typename TIN, int KIND, int NOUT>
-__device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TIN r1, double (&acc)[NOUT]) {
+__device__ __forceinline__ void accumulate(const CtbTr& tr, double w, TIN r0, TIN r1, bool on, double (&acc)[NOUT]) {
   double f[NOUT];
   ctb_apply<KIND, NOUT>(tr, (double)r0, (double)r1, f);
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) {
     const double p = w * f[j];
-    if (p == p) acc[j] += p;
+    if (on && p == p) acc[j] += p;
   }
 }
 
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(const AggArgs a) {
     const int64_t tp = tv ? (a.tix ? a.tix[t] : t) : 0;
     int tg, tg0;
     lane_group(a, t, tv, tg, tg0);
+    const int doy = (a.doy && tv) ? __ldg(a.doy + a.t_off + t) : 0;
     double acc[NOUT];
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) acc[j] = 0.0;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(const AggArgs a) {
         x0 = (double)__ldg(X0 + off);
         if constexpr (NIN == 2) x1 = (double)__ldg(X1 + off);
       }
-      accumulate<double, KIND, NOUT>(a.tr, w, x0, x1, acc);
+      accumulate<double, KIND, NOUT>(a.tr, w, x0, x1, a.doy ? ctb_gate_on(__ldg(a.gate + e), doy) : true, acc);
     }
     // 1/den: the same normalisation as the staged kernels (0 * inf = NaN, x * inf = +-inf)
     ctb_emit<NOUT>(a, r, 1.0 / a.den[r], acc, lane, t, tv, tb, tg, tg0);
@@ -188,9 +189,13 @@ size_t gpart_bytes(const ctb_plan* plan, const ctb_time_groups* g, int n_out) {
 int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype, int layout,
                    int64_t stride, const int32_t* time_index, int64_t T, int transform,
                    const double* params, int n_params, int n_out, const ctb_time_groups* G,
-                   int64_t t_begin, int flush, double* out,
+                   int64_t t_begin, int flush, const int32_t* day_of_year, double* out,
                    int64_t out_ld, void* workspace, size_t workspace_bytes, int variant, void* stream) {
   const char* fn = G ? "ctb_aggregate_grouped" : "ctb_aggregate";
+  if (day_of_year && P && !P->has_gate) {
+    ctb_set_error("%s: day_of_year given, but the plan was built without ctb_plan_opts.cell_gate", fn);
+    return CTB_ERR_INVALID;
+  }
   if (!P || !x0 || (!out && T > 0 && P->R > 0)) { ctb_set_error("%s: null argument", fn); return CTB_ERR_INVALID; }
   const int64_t n_cols = G ? G->n_groups : T;
   if (out_ld == 0) out_ld = n_cols;
@@ -245,6 +250,7 @@ int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype,
   a.n_split = P->n_split;
   a.n_tb = (int)((T + CTB_TB - 1) / CTB_TB);
   a.scratch_ld = T;
+  a.doy = day_of_year; a.gate = P->d_gate;
   if (G) {
     a.tgroup = G->d_group; a.gk = G->gk; a.n_groups = G->n_groups; a.g_t_lo = G->d_t_lo; a.g_t_hi = G->d_t_hi;
     a.g_ntb = (int)((G->T + CTB_TB - 1) / CTB_TB); a.t_off = (int)t_begin; a.scratch_ld = G->T;
@@ -330,7 +336,7 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
                              double* out, int64_t out_ld, void* workspace,
                              size_t workspace_bytes, int variant, void* stream) {
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
-                        nullptr, 0, 1, out, out_ld, workspace, workspace_bytes, variant, stream);
+                        nullptr, 0, 1, nullptr, out, out_ld, workspace, workspace_bytes, variant, stream);
 }
 
 // ------------------------------------------------------------ time groups ---
@@ -398,5 +404,17 @@ extern "C" int ctb_aggregate_grouped(const ctb_plan* P, const void* x0, const vo
                                      void* workspace, size_t workspace_bytes, int variant, void* stream) {
   if (!groups) { ctb_set_error("ctb_aggregate_grouped: null time groups"); return CTB_ERR_INVALID; }
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
-                        groups, t_begin, flush, out, out_ld, workspace, workspace_bytes, variant, stream);
+                        groups, t_begin, flush, nullptr, out, out_ld, workspace, workspace_bytes, variant, stream);
+}
+
+extern "C" int ctb_aggregate_ex(const ctb_plan* P, const void* x0, const void* x1, int dtype, int layout,
+                                int64_t stride, const int32_t* time_index, int64_t T, int transform,
+                                const double* params, int n_params, int n_out, const ctb_agg_opts* opts,
+                                double* out, int64_t out_ld, void* workspace, size_t workspace_bytes,
+                                int variant, void* stream) {
+  const ctb_agg_opts none{};
+  const ctb_agg_opts& o = opts ? *opts : none;
+  return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
+                        o.groups, o.groups ? o.t_begin : 0, o.groups ? o.flush : 1, o.day_of_year, out, out_ld,
+                        workspace, workspace_bytes, variant, stream);
 }

@@ -60,8 +60,16 @@ struct CtbSeg {
 struct CtbEnt {
   double w;        // effective weight of the weights row (aggregations.py:73)
   uint32_t off;    // byte offset of the staged gridcell's column in a tile row: column * elem_bytes
-  uint32_t pad;
+  uint32_t gate;   // growing-season gate of the gridcell (ctb_gate_on), CTB_GATE_ALWAYS without a mask
 };
+
+// Growing-season gate (utils.py:83-153): first day | last day << 9 | wrap << 18.  A gridcell-day counts
+// when (first <= day_of_year <= last) != wrap; an empty interval gives "never" (wrap = 0: planting date
+// missing) or "always" (wrap = 1: harvest date missing).
+constexpr uint32_t CTB_GATE_ALWAYS = 0u | (511u << 9);
+__host__ __device__ __forceinline__ bool ctb_gate_on(uint32_t g, int doy) {
+  return ((doy >= (int)(g & 511u)) & (doy <= (int)((g >> 9) & 511u))) != (bool)(g >> 18);
+}
 static_assert(sizeof(CtbBlobHeader) == 32 && sizeof(CtbSeg) == 16 && sizeof(CtbEnt) == 16, "blob layout");
 
 // A bundle stages at most CTB_TILE_UNITS 16-byte units per day and input.
@@ -99,6 +107,8 @@ struct ctb_plan {
   int32_t* d_row_ptr = nullptr;   // [R+1]
   int32_t* d_col = nullptr;       // [nnz]
   double* d_w = nullptr;          // [nnz]
+  uint32_t* d_gate = nullptr;     // [nnz] growing-season gate of every kept row's gridcell
+  int has_gate = 0;
   double* d_den = nullptr;        // [R]
 
   // staging bundles (device)
@@ -301,6 +311,9 @@ struct AggArgs {
   int n_groups;
   const int32_t *g_t_lo, *g_t_hi;   // [n_groups] day range of every output column
   int64_t scratch_ld;      // days per partial row of a split region (T, or T_total with time groups)
+  // growing-season gate: day of year of day t_off + t; NULL = no gate.  gate: per CSR entry (direct kernel)
+  const int32_t* doy;
+  const uint32_t* gate;
   const int32_t *row_ptr, *col;
   const double* w;
   const int32_t *split_region, *split_slot_ptr;
@@ -341,7 +354,7 @@ __device__ __forceinline__ void ctb_emit(const AggArgs& a, int target, double rd
 }
 
 // ctb_stream.cu: the streaming kernel (IDENTITY / POLY, 16-byte aligned TIME_MAJOR planes)
-int ctb_launch_stream(const ctb_plan* P, const AggArgs& a, int dtype, int kind, int n_out, cudaStream_t st);
+int ctb_launch_stream(const ctb_plan* P, const AggArgs& a, int dtype, int kind, int n_out, cudaStream_t st);   // a.doy != NULL: gated
 
 // RAII: make the plan's device current for the duration of an entry point
 struct CtbDeviceGuard {

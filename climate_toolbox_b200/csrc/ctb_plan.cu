@@ -142,7 +142,7 @@ struct BundleBuilder {
 
   // bundle under construction
   std::vector<int32_t> cur_pieces;  // unsorted, unique
-  struct Seg { int32_t target; std::vector<int32_t> cols; std::vector<double> ws; };
+  struct Seg { int32_t target; std::vector<int32_t> cols; std::vector<double> ws; std::vector<uint32_t> gates; };
   std::vector<Seg> cur_segs;
   int32_t cur_ent_pad = 0;
 
@@ -258,6 +258,7 @@ struct BundleBuilder {
       for (int32_t k = 0; k < n; ++k) {
         ent[e + k].w = s.ws[order[k]];
         ent[e + k].off = (uint32_t)colq[order[k]] * (uint32_t)elem_bytes;
+        ent[e + k].gate = s.gates[order[k]];
       }
       // padding of the last quad: weight 0 on a copy of the quad's first entry -- the same shared
       // address (a broadcast, no bank conflict) and a value of the region's own (a NaN elsewhere in
@@ -265,6 +266,7 @@ struct BundleBuilder {
       for (int32_t k = n; k < pad(n, 4); ++k) {
         ent[e + k].w = 0.0;
         ent[e + k].off = ent[e + (n & ~3)].off;
+        ent[e + k].gate = ent[e + (n & ~3)].gate;
       }
       e += pad(n, 4);
     }
@@ -294,7 +296,7 @@ extern "C" void ctb_plan_free(ctb_plan* p) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
-  cudaFree(p->d_row_cell); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_w);
+  cudaFree(p->d_row_cell); cudaFree(p->d_row_ptr); cudaFree(p->d_col); cudaFree(p->d_w); cudaFree(p->d_gate);
   cudaFree(p->d_den); cudaFree(p->d_b_blob_off); cudaFree(p->d_b_desc); cudaFree(p->d_unit_tab); cudaFree(p->d_work_counter); cudaFree(p->d_pack_src);
   cudaFree(p->d_blob); cudaFree(p->d_split_region); cudaFree(p->d_split_slot_ptr);
   cudaSetDevice(prev);
@@ -445,8 +447,12 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   // numerator (NaN product is skipped; 0*x is 0 or NaN) and are already in den.
   std::vector<int32_t> row_ptr(R + 1, 0), col;
   std::vector<double> w;
+  std::vector<uint32_t> gate;     // growing-season gate of every kept row's PHYSICAL gridcell
+  const uint32_t* cell_gate = opts ? opts->cell_gate : nullptr;
+  P->has_gate = cell_gate ? 1 : 0;
   col.reserve(n_rows);
   w.reserve(n_rows);
+  gate.reserve(n_rows);
   int32_t max_rows = 0;
   for (int32_t r = 0; r < R; ++r) {
     for (int32_t k = rp_all[r]; k < rp_all[r + 1]; ++k) {
@@ -455,6 +461,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
       if (ww == ww && ww != 0.0) {
         col.push_back(P->h_row_cell[row]);
         w.push_back(ww);
+        gate.push_back(cell_gate ? cell_gate[P->h_row_cell[row]] : CTB_GATE_ALWAYS);
       }
     }
     row_ptr[r + 1] = (int32_t)col.size();
@@ -557,11 +564,12 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   int32_t n_scratch = 0;
   std::vector<int32_t> newp;
 
-  auto add_segment = [&](int32_t target, const int32_t* cols, const double* ws, int32_t n) {
+  auto add_segment = [&](int32_t target, const int32_t* cols, const double* ws, const uint32_t* gs, int32_t n) {
     BundleBuilder::Seg s;
     s.target = target;
     s.cols.assign(cols, cols + n);
     s.ws.assign(ws, ws + n);
+    s.gates.assign(gs, gs + n);
     for (int32_t k = 0; k < n; ++k) {
       const int32_t p = cols[k] / CTB_PIECE;
       if (stamp[p] != gen) { stamp[p] = gen; B.cur_pieces.push_back(p); }
@@ -580,7 +588,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
     std::sort(newp.begin(), newp.end());
     newp.erase(std::unique(newp.begin(), newp.end()), newp.end());
     if (B.fits((int32_t)newp.size(), n)) {
-      add_segment(g.r, &col[g.e0], &w[g.e0], n);
+      add_segment(g.r, &col[g.e0], &w[g.e0], &gate[g.e0], n);
       continue;
     }
     // does it fit an empty bundle?
@@ -592,7 +600,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
     B.close();
     ++gen;
     if (B.fits((int32_t)own.size(), n)) {
-      add_segment(g.r, &col[g.e0], &w[g.e0], n);
+      add_segment(g.r, &col[g.e0], &w[g.e0], &gate[g.e0], n);
       continue;
     }
     // split: order the region's rows by cell, cut into fragments that fit one tile
@@ -602,15 +610,16 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
                      [&](int a, int b) { return col[g.e0 + a] < col[g.e0 + b]; });
     std::vector<int32_t> fc;
     std::vector<double> fw;
+    std::vector<uint32_t> fg;
     int32_t fpieces = 0, last_piece = -1;
     split_region.push_back(g.r);
     auto flush = [&]() {
       if (fc.empty()) return;
-      add_segment(~n_scratch, fc.data(), fw.data(), (int32_t)fc.size());
+      add_segment(~n_scratch, fc.data(), fw.data(), fg.data(), (int32_t)fc.size());
       ++n_scratch;
       B.close();
       ++gen;
-      fc.clear(); fw.clear(); fpieces = 0; last_piece = -1;
+      fc.clear(); fw.clear(); fg.clear(); fpieces = 0; last_piece = -1;
     };
     for (int32_t q = 0; q < n; ++q) {
       const int32_t c = col[g.e0 + idx[q]];
@@ -622,6 +631,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
       if (p != last_piece) { ++fpieces; last_piece = p; }
       fc.push_back(c);
       fw.push_back(w[g.e0 + idx[q]]);
+      fg.push_back(gate[g.e0 + idx[q]]);
     }
     flush();
     split_slot_ptr.push_back(n_scratch);
@@ -643,6 +653,7 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   if ((rc = upload(&P->d_row_ptr, row_ptr))) return rc;
   if ((rc = upload(&P->d_col, col))) return rc;
   if ((rc = upload(&P->d_w, w))) return rc;
+  if ((rc = upload(&P->d_gate, gate))) return rc;
   if ((rc = upload(&P->d_b_blob_off, B.b_blob_off))) return rc;
   if ((rc = upload(&P->d_blob, B.blob))) return rc;
   if ((rc = upload(&P->d_b_desc, B.desc))) return rc;

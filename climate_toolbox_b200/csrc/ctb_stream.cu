@@ -176,13 +176,13 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
 // acc[j] += w * f_j(x) for one staged value; CHECK: products that are NaN are skipped and so
 // are the zero-weight padding entries (aggregations.py:78: skipna sum of x * w)
 template <typename TIN, int KIND, int NOUT, bool CHECK>
-__device__ __forceinline__ void add_value(const CtbTr& tr, double w, TIN x, double (&acc)[NOUT]) {
+__device__ __forceinline__ void add_value(const CtbTr& tr, double w, TIN x, bool on, double (&acc)[NOUT]) {
   if constexpr (KIND == CTB_TR_IDENTITY) {
     if constexpr (CHECK) {
       const double p = w * (double)x;
-      if (w != 0.0 && p == p) acc[0] += p;
+      if (on && w != 0.0 && p == p) acc[0] += p;
     } else {
-      acc[0] = fma(w, (double)x, acc[0]);
+      if (on) acc[0] = fma(w, (double)x, acc[0]);
     }
   } else {
     double f[NOUT];
@@ -191,12 +191,19 @@ __device__ __forceinline__ void add_value(const CtbTr& tr, double w, TIN x, doub
     for (int j = 0; j < NOUT; ++j) {
       if constexpr (CHECK) {
         const double p = w * f[j];
-        if (w != 0.0 && p == p) acc[j] += p;
+        if (on && w != 0.0 && p == p) acc[j] += p;
       } else {
-        acc[j] = fma(w, f[j], acc[j]);
+        if (on) acc[j] = fma(w, f[j], acc[j]);
       }
     }
   }
+}
+
+// growing-season gate of the lane's entry on its four days (GATE = false: always on, folded away)
+template <bool GATE>
+__device__ __forceinline__ void gate4(uint32_t g, const int (&doy)[4], bool (&on)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) on[k] = GATE ? ctb_gate_on(g, doy[k]) : true;
 }
 
 // fold the four entry lanes (lane bits 3, 4) of the four day-group accumulators:
@@ -215,9 +222,9 @@ __device__ __forceinline__ double fold_quads(double a0, double a1, double a2, do
 // One region (segment) of one tile.  tile_a: shared address of the lane's row d8; ent_a: shared
 // address of the lane's entry of the first quad.  Returns v[j] = sum over the region's entries
 // of w * f_j(x[day = lane]).
-template <typename TIN, int KIND, int NOUT, bool CHECK>
+template <typename TIN, int KIND, int NOUT, bool CHECK, bool GATE>
 __device__ __forceinline__ void reduce_region(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
-                                              int lane, double (&v)[NOUT]) {
+                                              int lane, const int (&doy)[4], double (&v)[NOUT]) {
   constexpr int CTB_ROWB = Geo<1>::ROWB;
   double acc[4][NOUT];
 #pragma unroll
@@ -233,10 +240,12 @@ __device__ __forceinline__ void reduce_region(const CtbTr& tr, uint32_t tile_a, 
     const TIN x1 = lds_val<TIN>(xa + 8 * CTB_ROWB);
     const TIN x2 = lds_val<TIN>(xa + 16 * CTB_ROWB);
     const TIN x3 = lds_val<TIN>(xa + 24 * CTB_ROWB);
-    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x0, acc[0]);
-    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x1, acc[1]);
-    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x2, acc[2]);
-    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x3, acc[3]);
+    bool on[4];
+    gate4<GATE>(m.w, doy, on);
+    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x0, on[0], acc[0]);
+    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x1, on[1], acc[1]);
+    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x2, on[2], acc[2]);
+    add_value<TIN, KIND, NOUT, CHECK>(tr, w, x3, on[3], acc[3]);
   }
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) v[j] = fold_quads(acc[0][j], acc[1][j], acc[2][j], acc[3][j], lane);
@@ -250,9 +259,9 @@ __device__ __forceinline__ void reduce_region(const CtbTr& tr, uint32_t tile_a, 
 // min / max of the raw bit patterns (one ALU instruction per value) tells whether the region-tile
 // saw anything else -- zero, a denormal, a negative number, an infinity or a NaN -- and then the
 // caller reduces it again with the exact loops.  Returns false in that case.
-template <int KIND, int NOUT>
+template <int KIND, int NOUT, bool GATE>
 __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
-                                                    int lane, double (&v)[NOUT]) {
+                                                    int lane, const int (&doy)[4], double (&v)[NOUT]) {
   constexpr int CTB_ROWB = Geo<1>::ROWB;
   double acc[4][NOUT];
 #pragma unroll
@@ -277,16 +286,19 @@ __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t ti
     bmin = __vimin3_u32(bmin, b2, b3);
     bmax = __vimax3_u32(bmax, b2, b3);
     const uint32_t bb[4] = {b0, b1, b2, b3};
+    bool on[4];
+    gate4<GATE>(m.w, doy, on);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const double x = widen(bb[g]);
       if constexpr (KIND == CTB_TR_IDENTITY) {
-        acc[g][0] = fma(w, x, acc[g][0]);
+        if (on[g]) acc[g][0] = fma(w, x, acc[g][0]);
       } else {
         double f[NOUT];
         ctb_apply<KIND, NOUT>(tr, x, 0.0, f);
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) acc[g][j] = fma(w, f[j], acc[g][j]);
+        for (int j = 0; j < NOUT; ++j)
+          if (on[g]) acc[g][j] = fma(w, f[j], acc[g][j]);
       }
     }
   }
@@ -299,9 +311,9 @@ __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t ti
 // Two-input transforms (Snyder EDD / GDD from tasmin, tasmax): the same quad loop, the lane's entry
 // evaluated on its four days.  fp64 ALU bound; NaN results are skipped by a select (the reference's
 // skipna sum), and the zero-weight padding of the last quad never meets a value (0 * inf).
-template <typename TIN, int KIND, int NOUT>
+template <typename TIN, int KIND, int NOUT, bool GATE>
 __device__ __forceinline__ void reduce_region2(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
-                                               int lane, double (&v)[NOUT]) {
+                                               int lane, const int (&doy)[4], double (&v)[NOUT]) {
   constexpr int ROWB = Geo<2>::ROWB, IN_BYTES = Geo<2>::IN_BYTES;
   double acc[4][NOUT];
 #pragma unroll
@@ -319,19 +331,22 @@ __device__ __forceinline__ void reduce_region2(const CtbTr& tr, uint32_t tile_a,
       lo[g] = lds_val<TIN>(xa + g * 8 * ROWB);
       hi[g] = lds_val<TIN>(xa + IN_BYTES + g * 8 * ROWB);
     }
+    bool on[4];
+    gate4<GATE>(m.w, doy, on);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       double f[NOUT];
       ctb_apply<KIND, NOUT>(tr, (double)lo[g], (double)hi[g], f);
 #pragma unroll
-      for (int j = 0; j < NOUT; ++j) acc[g][j] = fma(w, (wnz && f[j] == f[j]) ? f[j] : 0.0, acc[g][j]);
+      for (int j = 0; j < NOUT; ++j)
+        acc[g][j] = fma(w, (wnz && on[g] && f[j] == f[j]) ? f[j] : 0.0, acc[g][j]);
     }
   }
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) v[j] = fold_quads(acc[0][j], acc[1][j], acc[2][j], acc[3][j], lane);
 }
 
-template <typename TIN, int KIND, int NOUT, int THREADS, int S, bool GROUPS>
+template <typename TIN, int KIND, int NOUT, int THREADS, int S, bool GATE>
 __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a) {
   constexpr int NIN = NIn<KIND>::v;
   using G = Geo<NIN>;
@@ -519,9 +534,17 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
       const int t = (int)d.x + lane;
       const bool valid = t < a.T;
       int tg = -1, tg0 = 0;
-      if constexpr (GROUPS) {
+      if (a.tgroup) {
         tg = valid ? __ldg(a.tgroup + a.t_off + t) : -1;
         tg0 = __shfl_sync(0xffffffffu, tg, 0);
+      }
+      int doy[4] = {0, 0, 0, 0};   // day of year of the lane's four days d8 + 8 g (growing-season gate)
+      if constexpr (GATE) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int tt = (int)d.x + d8 + 8 * g;
+          doy[g] = tt < a.T ? __ldg(a.doy + a.t_off + tt) : 0;
+        }
       }
       double* const out_t = a.out + t;
       for (int s = rot; s < n_seg;) {
@@ -533,20 +556,20 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
         double v[NOUT];
         bool done = false;
         if constexpr (NIN == 2) {
-          reduce_region2<TIN, KIND, NOUT>(a.tr, tile_a, ea, nq, lane, v);
+          reduce_region2<TIN, KIND, NOUT, GATE>(a.tr, tile_a, ea, nq, lane, doy, v);
           done = true;
         } else if constexpr (sizeof(TIN) == 4) {
-          done = reduce_region_widen<KIND, NOUT>(a.tr, tile_a, ea, nq, lane, v);
+          done = reduce_region_widen<KIND, NOUT, GATE>(a.tr, tile_a, ea, nq, lane, doy, v);
         }
         if constexpr (NIN == 1) if (!done) {
-          reduce_region<TIN, KIND, NOUT, false>(a.tr, tile_a, ea, nq, lane, v);
+          reduce_region<TIN, KIND, NOUT, false, GATE>(a.tr, tile_a, ea, nq, lane, doy, v);
           bool bad = false;
 #pragma unroll
           for (int j = 0; j < NOUT; ++j) bad |= !(fabs(v[j]) <= 1.7976931348623157e308);
           if (__any_sync(0xffffffffu, bad && valid))
-            reduce_region<TIN, KIND, NOUT, true>(a.tr, tile_a, ea, nq, lane, v);
+            reduce_region<TIN, KIND, NOUT, true, GATE>(a.tr, tile_a, ea, nq, lane, doy, v);
         }
-        if constexpr (GROUPS) {
+        if (a.tgroup) {
           ctb_emit<NOUT>(a, target, rden, v, lane, t, valid, (int)d.z, tg, tg0);
         } else if (valid) {
           if (target >= 0) {
@@ -587,13 +610,13 @@ int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   static int n_sm[64] = {0};
   static bool attr_set[64][2] = {{false}};
   const int dev = P->device & 63;
-  const bool groups = a.tgroup != nullptr;
-  auto k = groups ? agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, true>
-                  : agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, false>;
-  if (!attr_set[dev][groups]) {
+  const bool gate = a.doy != nullptr;   // growing-season gate: its own instantiation (the inner loop tests it)
+  auto k = gate ? agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, true>
+                : agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, false>;
+  if (!attr_set[dev][gate]) {
     CTB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, P->device));
     CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set[dev][groups] = true;
+    attr_set[dev][gate] = true;
   }
   a.n_stages = S;
   a.tile_stride = Geo<NIN>::TILE_BYTES;

@@ -76,6 +76,11 @@ typedef struct ctb_plan_opts {
   int32_t elem_bytes;               /* 4 (default) or 8: element size of the inputs this plan will
                                        aggregate (staged-cell byte offsets are baked into the plan) */
   int32_t reserved[4];
+  const uint32_t* cell_gate;        /* HOST [nlat_phys * nlon_phys], nullable: growing-season gate of every
+                                       physical gridcell, first_day | last_day << 9 | wrap << 18 (day of year
+                                       0..511): the gridcell-day counts when (first <= doy <= last) != wrap.
+                                       Replaces the lat x lon x time mask of utils.py:83-153; applied by
+                                       ctb_aggregate_ex when day_of_year is given */
 } ctb_plan_opts;
 
 typedef struct ctb_plan_info {
@@ -161,6 +166,27 @@ int ctb_aggregate(const ctb_plan* plan, const void* x0, const void* x1, int dtyp
                   const double* params, int n_params, int n_out, double* out, int64_t out_ld,
                   void* workspace, size_t workspace_bytes, int variant, void* stream);
 
+/* ---- everything at once: time reduction and/or growing-season gate ---------- *
+ * opts->groups / t_begin / flush: as ctb_aggregate_grouped below.  opts->day_of_year: DEVICE int32,
+ * day of year of every day of the time axis ([T], or [groups' T] with a window); with it, gridcell-days
+ * outside their gridcell's growing season (ctb_plan_opts.cell_gate) do not enter the numerator -- the
+ * fused form of multiplying the data by get_daily_growing_season_mask (utils.py:119-153), whose 0 and
+ * NaN both leave the weighted sum untouched while the weight still counts in the denominator. */
+typedef struct ctb_time_groups ctb_time_groups;
+typedef struct ctb_agg_opts {
+  const ctb_time_groups* groups;
+  int64_t t_begin;
+  int32_t flush;
+  int32_t reserved;
+  const int32_t* day_of_year;
+} ctb_agg_opts;
+int ctb_aggregate_ex(const ctb_plan* plan, const void* x0, const void* x1, int dtype, int layout,
+                     int64_t stride, const int32_t* time_index, int64_t T, int transform,
+                     const double* params, int n_params, int n_out, const ctb_agg_opts* opts,
+                     double* out, int64_t out_ld, void* workspace, size_t workspace_bytes, int variant,
+                     void* stream);
+/* workspace of ctb_aggregate_ex: ctb_aggregate_workspace_bytes without groups, else the grouped one */
+
 /* ---- pointwise helpers (materialising what the reference materialises) --- */
 /* out[j][i] = f_j(x0[i], x1[i]) for i < n; DEVICE pointers (transformations.py:69-89,189). */
 int ctb_transform(const void* x0, const void* x1, int dtype, int64_t n, int transform,
@@ -205,7 +231,6 @@ int ctb_copy_rows_to_host(void* dst, size_t dst_pitch, const void* src, size_t s
  * relative to the window's inputs), with flush = 0 for all but the last call; the call with
  * flush != 0 (T may be 0) finishes the sums and writes `out`.  All calls share one workspace
  * (split-region rows + per-tile partial sums) and one stream. */
-typedef struct ctb_time_groups ctb_time_groups;
 int ctb_time_groups_create(const int32_t* group_of_day, int64_t T, int device, ctb_time_groups** out);
 void ctb_time_groups_free(ctb_time_groups* groups);
 int32_t ctb_time_groups_count(const ctb_time_groups* groups);

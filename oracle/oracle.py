@@ -46,6 +46,8 @@ import pandas as pd
 
 __all__ = [
     "time_group_sum",
+    "season_boundaries",
+    "growing_season_mask",
     "convert_lons_mono",
     "convert_lons_split",
     "leap_day_keep_mask",
@@ -289,3 +291,30 @@ def time_group_sum(values, dims, labels, time_dim="time"):
     parts = [np.take(values, np.arange(a, b), axis=ax).sum(axis=ax, keepdims=True) for a, b in zip(starts, ends)]
     out = np.concatenate(parts, axis=ax) if parts else np.take(values, [], axis=ax)
     return out, labels[change]
+
+
+# ---------------------------------------------------------------------------
+# growing-season mask
+# ---------------------------------------------------------------------------
+def season_boundaries(planting, harvest):
+    """/root/reference/climate_toolbox/utils/utils.py:83-116 on plain arrays [lat][lon]: the two z planes
+    sorted per gridcell (np.sort: NaN last) -> (min_day, max_day)."""
+    both = np.sort(np.stack([np.asarray(planting, float), np.asarray(harvest, float)], axis=2), axis=2)
+    return both[:, :, 0], both[:, :, 1]
+
+
+def growing_season_mask(planting, harvest, day_of_year):
+    """utils.py:119-153 on plain arrays: the dense [lat][lon][time] mask of 1 / 0 / NaN.
+    ``mask = (doy >= min) & (doy <= max)``; ``.where(harvest >= planting)`` blanks wrap-around seasons
+    (and gridcells with a missing date), ``.fillna(1 - mask)`` fills those with the complement,
+    ``.where(~isnan(planting))`` blanks gridcells without a planting date."""
+    planting, harvest = np.asarray(planting, float), np.asarray(harvest, float)
+    mn, mx = season_boundaries(planting, harvest)
+    doy = np.asarray(day_of_year)[None, None, :]
+    with np.errstate(invalid="ignore"):
+        mask = ((doy >= mn[:, :, None]) & (doy <= mx[:, :, None])).astype(np.float64)
+        keep = (harvest >= planting)[:, :, None]
+    out = np.where(keep, mask, np.nan)
+    out = np.where(np.isnan(out), 1.0 - mask, out)
+    out = np.where(np.isnan(planting)[:, :, None], np.nan, out)
+    return out

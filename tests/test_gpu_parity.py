@@ -725,6 +725,72 @@ def test_time_groups_blocks_and_split_regions():
 
 
 # ----------------------------------------------------------------------------
+# growing-season mask fused into the kernel (reference utils.py:83-153)
+# ----------------------------------------------------------------------------
+def _calendar(lat, lon_std, rng):
+    """Crop calendar on the grid of the data, stored the reference's way: longitudes on 0..360 (= +180)."""
+    nlat, nlon = len(lat), len(lon_std)
+    plant = rng.integers(1, 366, (nlat, nlon)).astype(np.float64)
+    harv = rng.integers(1, 366, (nlat, nlon)).astype(np.float64)
+    harv[rng.random((nlat, nlon)) < 0.05] = np.nan
+    plant[rng.random((nlat, nlon)) < 0.05] = np.nan
+    gd = Dataset({"variable": (("z", "latitude", "longitude"), np.stack([plant, harv]))},
+                 coords={"z": np.array([1, 2]), "latitude": lat, "longitude": lon_std + 180})
+    return gd, plant, harv
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("kind", ["identity", "edd_annual", "cell_major", "lon360_leap"])
+def test_growing_season_mask_fused(where, kind):
+    """aggregate(ds, season_mask=m) == oracle aggregate of x * dense mask (1 / 0 / NaN)."""
+    from climate_toolbox_b200.utils.utils import get_daily_growing_season_mask, remove_leap_days
+    rng = np.random.default_rng(21)
+    T = 420 if kind == "edd_annual" else 75
+    lat, lon, df, tas, tmin, tmax = _config(1.0, 3000, T, lon_0_360=(kind == "lon360_leap"))
+    time = pd.date_range("2003-12-01" if kind != "lon360_leap" else "2004-02-01", periods=T)
+    lon_std = lon if kind != "lon360_leap" else oracle.convert_lons_split(lon)[0]
+    gd, plant, harv = _calendar(lat, lon_std, rng)
+    dims = ("time", "lat", "lon")
+    coords = {"time": time, "lat": lat, "lon": lon}
+    doy = time.dayofyear.values
+    dense = oracle.growing_season_mask(plant, harv, doy).transpose(2, 0, 1)        # (time, lat, lon) on lon_std
+    kw = {}
+    if kind == "identity":
+        ds = Dataset({"v": (dims, _put(tas, where))}, coords=coords)
+        f, fdims = tas.astype(np.float64), dims
+    elif kind == "cell_major":
+        fdims = ("lat", "lon", "time")
+        x = np.ascontiguousarray(tas.transpose(1, 2, 0))
+        ds = Dataset({"v": (fdims, _put(x, where))}, coords=coords)
+        f, dense = x.astype(np.float64), dense.transpose(1, 2, 0)
+    elif kind == "edd_annual":
+        tn = DataArray(_put(tmin, where), dims=dims, coords=coords, attrs={"units": "K"})
+        tx = DataArray(_put(tmax, where), dims=dims, coords=coords, attrs={"units": "K"})
+        ds = Dataset(coords=coords)
+        ds["v"] = snyder_edd(tn, tx, 288.15)
+        f, fdims = oracle.snyder_edd(tmin, tmax, 288.15), dims
+        kw = {"time_groups": "year"}
+    else:   # 0..360 longitudes (lazy roll) and a leap day removed (lazy time take): the gate follows both
+        ds = remove_leap_days(load_bcsd(Dataset({"v": (dims, _put(tas, where))}, coords=coords), "v"))
+        keep = ~((time.month == 2) & (time.day == 29))
+        _, perm = oracle.convert_lons_split(lon)
+        f, fdims = np.take(tas, perm, axis=2)[keep].astype(np.float64), dims
+        dense, time = dense[keep], time[keep]
+    m = get_daily_growing_season_mask(ds["lat"], ds["lon"], ds["time"], gd)
+    out = weighted_aggregate_grid_to_regions(ds, "v", "cropwt", "hierid", weights=df, season_mask=m, **kw)
+    ref, rd, labels, scale = oracle_agg(f * dense, fdims, lat, lon_std, df, "cropwt", "hierid")
+    scale = np.nan_to_num(scale)
+    if kw:
+        ref, years = oracle.time_group_sum(ref, rd, time.year.values)
+        scale, _ = oracle.time_group_sum(scale, rd, time.year.values)
+        assert list(out.time.values) == list(years)
+    assert out.v.dims == rd
+    check(out.v.values, ref, scale + 1e-300)
+    plain = weighted_aggregate_grid_to_regions(ds, "v", "cropwt", "hierid", weights=df, **kw)
+    assert not np.allclose(np.nan_to_num(plain.v.values), np.nan_to_num(out.v.values))      # the gate did something
+
+
+# ----------------------------------------------------------------------------
 # full size (BASELINE.json configs[1]): size-independent properties
 # ----------------------------------------------------------------------------
 def test_full_size_properties():

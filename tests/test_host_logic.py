@@ -186,3 +186,51 @@ def test_stacked_weight_columns_for_one_pass_multi_weight():
     for k, c in enumerate(cols):
         ref = oracle.weighted_aggregate_grid_to_regions(x, ("time", "lat", "lon"), lat, lon, df, c, "hierid")[0]
         np.testing.assert_allclose(got[:, k * R:(k + 1) * R], ref, rtol=1e-13, equal_nan=True)
+
+
+# ----------------------------------------------------------------------------
+# growing-season mask (reference utils.py:83-153): factored form vs the dense oracle
+# ----------------------------------------------------------------------------
+def _crop_calendar(nlat, nlon, rng, lon0=0.125, d=2.0):
+    """Synthetic crop calendar on the reference's 0..360 longitude convention: planting / harvest day per
+    gridcell, some seasons wrapping around the new year, fractional days, missing dates."""
+    from climate_toolbox_b200 import Dataset
+    lat = -90 + d / 2 + d * np.arange(nlat)
+    lon360 = lon0 + d * np.arange(nlon)
+    plant = rng.integers(1, 366, (nlat, nlon)).astype(np.float64)
+    harv = rng.integers(1, 366, (nlat, nlon)).astype(np.float64)        # about half of them < planting
+    plant[rng.random((nlat, nlon)) < 0.1] += 0.5
+    harv[rng.random((nlat, nlon)) < 0.05] = np.nan
+    plant[rng.random((nlat, nlon)) < 0.05] = np.nan
+    gd = Dataset({"variable": (("z", "latitude", "longitude"), np.stack([plant, harv]))},
+                 coords={"z": np.array([1, 2]), "latitude": lat, "longitude": lon360})
+    return gd, lat, lon360, plant, harv
+
+
+def test_growing_season_mask_matches_oracle():
+    import oracle
+    from climate_toolbox_b200.utils.utils import get_daily_growing_season_mask, season_boundaries
+    rng = np.random.default_rng(5)
+    gd, lat, lon360, plant, harv = _crop_calendar(12, 20, rng)
+    time = pd.date_range("2003-11-20", periods=120).values          # crosses the new year
+    lon = lon360 - 180                                               # the calendar's shift (utils.py:87)
+    order = np.argsort(lon)
+    mn, mx = season_boundaries(gd)
+    omn, omx = oracle.season_boundaries(plant[:, order], harv[:, order])
+    np.testing.assert_array_equal(mn.values, omn)
+    np.testing.assert_array_equal(mx.values, omx)
+    np.testing.assert_array_equal(mn.coords["longitude"].values, lon[order])
+    m = get_daily_growing_season_mask(lat, lon[order], time, gd)
+    assert m.shape == (12, 20, 120) and m.dims == ("lat", "lon", "time")
+    doy = pd.DatetimeIndex(time).dayofyear.values
+    ref = oracle.growing_season_mask(plant[:, order], harv[:, order], doy)
+    got = m.values
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_array_equal(np.nan_to_num(got, nan=-1), np.nan_to_num(ref, nan=-1))
+    assert np.isnan(ref).any() and (ref == 0).any() and (ref == 1).any()
+    # a subset / permutation of the grid's labels selects the matching gridcells; an unknown label raises
+    m2 = get_daily_growing_season_mask(lat[3:7], lon[order][::-1][:5], time, gd)
+    np.testing.assert_array_equal(np.nan_to_num(m2.values, nan=-1),
+                                  np.nan_to_num(ref[3:7][:, ::-1][:, :5], nan=-1))
+    with pytest.raises(KeyError):
+        get_daily_growing_season_mask(lat + 0.01, lon[order], time, gd)
