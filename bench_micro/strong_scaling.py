@@ -10,7 +10,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from climate_toolbox_b200 import _engine as E, synthetic  # noqa: E402
-from climate_toolbox_b200.parallel import aggregate_shard_overlapped  # noqa: E402
+from climate_toolbox_b200.parallel import PeerOutput, aggregate_shard_overlapped, aggregate_shard_p2p  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -50,6 +50,19 @@ recv = torch.empty((world * M, tl), device=dev, dtype=torch.float64)
 res["raw_all_gather"] = timed(lambda: dist.all_gather_into_tensor(recv, loc))
 full = torch.empty((M, world * tl), device=dev, dtype=torch.float64)
 res["strided_copy"] = timed(lambda: full.view(M, world, tl).copy_(recv.view(world, M, tl).permute(1, 0, 2)))
+ref, _ = aggregate_shard_overlapped(plan, x, None, x.shape[1], T, pieces=1)
+ref = ref.clone()
+try:
+    po = PeerOutput(plan, T)
+    res["p2p_fused"] = timed(lambda: aggregate_shard_p2p(plan, x, None, x.shape[1], T, po))
+    torch.cuda.synchronize()
+    ok = torch.equal(torch.nan_to_num(po.out), torch.nan_to_num(ref))
+    res["p2p_equal_to_nccl_gather"] = float(ok)
+    po.close()
+except Exception as ex:  # noqa: BLE001
+    res["p2p_error"] = -1.0
+    if rank == 0:
+        print("p2p failed:", repr(ex)[:300])
 if rank == 0:
     print("world", world, {k: round(v, 3) for k, v in res.items()}, "ms; bytes received per rank",
           8 * M * (T - tl))

@@ -321,10 +321,11 @@ def _workspace(plan, T, n_out, layout, variant, groups, workspace):
 
 
 def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out, variant, out, out_ld,
-            workspace, stream, groups=None, t_begin=0, flush=True, doy=None):
+            workspace, stream, groups=None, t_begin=0, flush=True, doy=None, peer_ptrs=None):
     """Raw-pointer call of ctb_aggregate_ex (p0/p1: device or mapped-host addresses).  With ``groups``
     the result is [n_out, R, n_groups]; ``doy`` (int array, day of year of every day of the time axis)
-    switches the growing-season gate of a plan built with ``cell_gate`` on."""
+    switches the growing-season gate of a plan built with ``cell_gate`` on; ``peer_ptrs`` (device
+    addresses laid out like ``out``) makes the kernel store every result to all of them."""
     dev = plan.device
     L = N.lib()
     if out is None:
@@ -338,6 +339,9 @@ def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out
     o.groups = groups._h if groups is not None else None
     o.t_begin, o.flush = int(t_begin), 1 if flush else 0
     o.day_of_year = doy_d.data_ptr() if doy_d is not None else None
+    if peer_ptrs:
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        o.peer_out, o.n_peer_out = arr, len(peer_ptrs)
     rc = L.ctb_aggregate_ex(
         plan._h, C.c_void_p(p0), C.c_void_p(p1) if p1 else None, ctb_dtype, layout, int(stride),
         C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
@@ -351,7 +355,7 @@ def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out
 
 def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", params=(), n_out=1,
                      variant=N.VARIANT_AUTO, out=None, out_ld=0, stream=None, workspace=None, groups=None,
-                     t_begin=0, flush=True, doy=None):
+                     t_begin=0, flush=True, doy=None, peer_ptrs=None):
     """Launch the fused kernel on device-resident inputs.
 
     ``x0`` / ``x1``: contiguous CUDA tensors (f32/f64).  ``tix``: numpy int array of
@@ -367,7 +371,7 @@ def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", para
         raise ValueError("the two inputs must agree in dtype and shape")
     return _launch(plan, x0.data_ptr(), x1.data_ptr() if x1 is not None else 0, _T2CTB[x0.dtype], layout,
                    stride, tix, T, kind, params, n_out, variant, out, out_ld, workspace, stream, groups,
-                   t_begin, flush, doy)
+                   t_begin, flush, doy, peer_ptrs)
 
 
 def _all_pinned(xs):

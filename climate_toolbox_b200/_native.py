@@ -26,6 +26,7 @@ SYMBOLS = (
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
     "ctb_host_pack", "ctb_pull_pack", "ctb_copy_rows_to_host", "ctb_time_groups_create", "ctb_time_groups_free", "ctb_time_groups_count",
     "ctb_aggregate_grouped_workspace_bytes", "ctb_aggregate_grouped", "ctb_aggregate_ex",
+    "ctb_ipc_alloc", "ctb_ipc_open", "ctb_ipc_close", "ctb_ipc_free",
 )
 
 
@@ -36,8 +37,12 @@ class PlanOpts(C.Structure):
 
 
 class AggOpts(C.Structure):
-    _fields_ = [("groups", C.c_void_p), ("t_begin", C.c_int64), ("flush", C.c_int32), ("reserved", C.c_int32),
-                ("day_of_year", C.c_void_p)]
+    _fields_ = [("groups", C.c_void_p), ("t_begin", C.c_int64), ("flush", C.c_int32), ("n_peer_out", C.c_int32),
+                ("day_of_year", C.c_void_p), ("peer_out", C.POINTER(C.c_void_p))]
+
+
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
 
 
 GATE_ALWAYS = 511 << 9
@@ -102,6 +107,14 @@ def lib():
     L.ctb_aggregate_ex.restype = C.c_int
     L.ctb_aggregate_ex.argtypes = [p, vp, vp, C.c_int, C.c_int, i64, vp, i64, C.c_int, dp, C.c_int,
                                    C.c_int, C.POINTER(AggOpts), vp, i64, vp, C.c_size_t, C.c_int, vp]
+    L.ctb_ipc_alloc.restype = C.c_int
+    L.ctb_ipc_alloc.argtypes = [C.c_size_t, C.c_int, C.POINTER(vp), vp]
+    L.ctb_ipc_open.restype = C.c_int
+    L.ctb_ipc_open.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.ctb_ipc_close.restype = C.c_int
+    L.ctb_ipc_close.argtypes = [vp, C.c_int]
+    L.ctb_ipc_free.restype = C.c_int
+    L.ctb_ipc_free.argtypes = [vp, C.c_int]
     L.ctb_transform.restype = C.c_int
     L.ctb_transform.argtypes = [vp, vp, C.c_int, i64, C.c_int, dp, C.c_int, C.c_int, vp, vp]
     L.ctb_gather_rows.restype = C.c_int

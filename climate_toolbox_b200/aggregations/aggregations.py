@@ -485,20 +485,33 @@ def weighted_aggregate_grid_to_regions(ds, variable, aggwt, agglev, weights=None
                                    **engine_opts), like)
 
 
-def _stack_weight_columns(weights, aggwts, agglev, backup_aggwt):
-    """One frame with a copy of the rows per weight column: region r under column k becomes the
-    virtual region ``k * R + code(r)``.  Returns (frame[lat, lon, _lev, _w, _bk], sorted region
-    labels, sorted virtual codes that have rows)."""
-    codes, labels = E.region_codes(weights[agglev].values)
-    R, K = len(labels), len(aggwts)
-    virt = np.concatenate([np.where(codes >= 0, codes.astype(np.int64) + k * R, -1) for k in range(K)])
+def _stack_weight_columns(weights, aggwts, agglevs, backup_aggwt):
+    """One frame with a copy of the rows per (region level, weight column) pair: region r of level l
+    under weight k becomes the virtual region ``base[l, k] + code_l(r)``.  Returns (frame[lat, lon,
+    _lev, _w, _bk], {level: sorted region labels}, [(level, weight, base, R_level)], sorted virtual
+    codes that have rows)."""
+    n = len(weights)
+    lat = np.asarray(weights["lat"].values, dtype=np.float64)
+    lon = np.asarray(weights["lon"].values, dtype=np.float64)
+    bk = np.asarray(weights[backup_aggwt].values, dtype=np.float64)
+    labels, combos, virt, ws = {}, [], [], []
+    base = 0
+    for lev in agglevs:
+        codes, labels[lev] = E.region_codes(weights[lev].values)
+        R = len(labels[lev])
+        for wt in aggwts:
+            combos.append((lev, wt, base, R))
+            virt.append(np.where(codes >= 0, codes.astype(np.int64) + base, -1))
+            ws.append(np.asarray(weights[wt].values, dtype=np.float64))
+            base += R
+    virt = np.concatenate(virt) if virt else np.zeros(0, dtype=np.int64)
+    K = len(combos)
     stacked = pd.DataFrame({
-        "lat": np.tile(np.asarray(weights["lat"].values, dtype=np.float64), K),
-        "lon": np.tile(np.asarray(weights["lon"].values, dtype=np.float64), K),
+        "lat": np.tile(lat, K), "lon": np.tile(lon, K),
         "_lev": np.where(virt >= 0, virt, np.nan),      # NaN labels are dropped, as in the reference
-        "_w": np.concatenate([np.asarray(weights[c].values, dtype=np.float64) for c in aggwts]),
-        "_bk": np.tile(np.asarray(weights[backup_aggwt].values, dtype=np.float64), K)})
-    return stacked, labels, np.unique(virt[virt >= 0])
+        "_w": np.concatenate(ws) if ws else np.zeros(0), "_bk": np.tile(bk, K)})
+    assert len(stacked) == n * K
+    return stacked, labels, combos, np.unique(virt[virt >= 0])
 
 
 _STACKED = {}   # (id(weights), columns) -> (weights ref, stacked frame): keeps the plan-cache fast path warm
@@ -507,44 +520,47 @@ _STACKED = {}   # (id(weights), columns) -> (weights ref, stacked frame): keeps 
 def weighted_aggregate_grid_to_regions_multi(ds, variable, aggwts, agglev, weights,
                                              backup_aggwt="areawt", **engine_opts):
     """
-    Extension: aggregate ``variable`` with SEVERAL weight columns in ONE pass over
-    the gridded data.  Equivalent to one ``weighted_aggregate_grid_to_regions`` call per entry of
-    ``aggwts`` (reference ``aggregations.py:87-124`` run once per weight), but the data is
-    staged once: every region is entered once per weight column as a "virtual" region
-    ``(k, region)``, the virtual regions of a region share their gridcell footprint and land in
-    the same kernel work bundle.
+    Extension: aggregate ``variable`` with SEVERAL weight columns and / or to SEVERAL
+    region levels in ONE pass over the gridded data.  Equivalent to one
+    ``weighted_aggregate_grid_to_regions`` call per (agglev, aggwt) pair (reference
+    ``aggregations.py:87-124`` run once per pair), but the data is staged once: every region is
+    entered once per pair as a "virtual" region, the virtual regions of a region share their
+    gridcell footprint and land in the same kernel work bundle; coarse levels (countries) are split
+    over bundles and summed in fixed order like any region larger than a tile.
 
-    Returns a Dataset with one variable per weight column named ``"<variable>_<aggwt>"``.
+    ``agglev``: one column name -> variables ``"<variable>_<aggwt>"`` over ``agglev`` (as before);
+    a list -> variables ``"<variable>_<aggwt>_<agglev>"``, each over its own region dimension.
     """
     if isinstance(weights, str):
         weights = prepare_spatial_weights_data(weights)
     aggwts = list(aggwts)
-    for col in ["lat", "lon", agglev, backup_aggwt] + aggwts:
+    single = isinstance(agglev, str)
+    agglevs = [agglev] if single else list(agglev)
+    for col in ["lat", "lon", backup_aggwt] + agglevs + aggwts:
         if col not in weights:
             raise KeyError(col)
     if not isinstance(variable, str):
         raise TypeError("weighted_aggregate_grid_to_regions_multi takes one variable name")
-    key = (id(weights), tuple(aggwts), agglev, backup_aggwt, len(weights))
+    key = (id(weights), tuple(aggwts), tuple(agglevs), backup_aggwt, len(weights))
     hit = _STACKED.get(key)
-    sums = tuple(E._col_fp(weights[c].values) for c in aggwts + [backup_aggwt, "lat", "lon", agglev])
+    sums = tuple(E._col_fp(weights[c].values) for c in aggwts + [backup_aggwt, "lat", "lon"] + agglevs)
     if hit is not None and hit[0] is weights and hit[2] == sums:
-        stacked, labels, present = hit[1], hit[3], hit[4]
+        stacked, labels, combos, present = hit[1], hit[3], hit[4], hit[5]
     else:
-        stacked, labels, present = _stack_weight_columns(weights, aggwts, agglev, backup_aggwt)
+        stacked, labels, combos, present = _stack_weight_columns(weights, aggwts, agglevs, backup_aggwt)
         if len(_STACKED) > 8:
             _STACKED.clear()
-        _STACKED[key] = (weights, stacked, sums, labels, present)
+        _STACKED[key] = (weights, stacked, sums, labels, combos, present)
     like = ds
     ds = from_any(ds)
     res = _aggregate_core(ds, [variable], "_w", "_lev", stacked, "_bk", trusted_weights=True, **engine_opts)
     var = res._vars[variable]
     ax = var.dims.index("_lev")
-    R, K = len(labels), len(aggwts)
     out = Dataset()
-    dims = tuple(agglev if d == "_lev" else d for d in var.dims)
     data = var.physical      # numpy (pinned block) or, with keep_on_device, the CUDA tensor itself
-    for k, w in enumerate(aggwts):
-        sel = np.flatnonzero((present >= k * R) & (present < (k + 1) * R))
+    for lev, wt, base, R in combos:
+        dims = tuple(lev if d == "_lev" else d for d in var.dims)
+        sel = np.flatnonzero((present >= base) & (present < base + R))
         if len(sel) and sel[-1] - sel[0] + 1 == len(sel):      # the usual case: a contiguous block -> a view
             idx = [slice(None)] * len(var.dims)
             idx[ax] = slice(int(sel[0]), int(sel[-1]) + 1)
@@ -553,8 +569,10 @@ def weighted_aggregate_grid_to_regions_multi(ds, variable, aggwts, agglev, weigh
             a = data.index_select(ax, torch.as_tensor(sel, device=data.device))
         else:
             a = np.take(data, sel, axis=ax)
-        out["{}_{}".format(variable, w)] = Variable(dims, a, var.attrs)
-    out._coords[agglev] = Variable((agglev,), np.asarray(labels))
+        name = "{}_{}".format(variable, wt) if single else "{}_{}_{}".format(variable, wt, lev)
+        out[name] = Variable(dims, a, var.attrs)
+    for lev in agglevs:
+        out._coords[lev] = Variable((lev,), np.asarray(labels[lev]))
     for d, c in res._coords.items():
         if d != "_lev":
             out._coords[d] = c

@@ -189,13 +189,19 @@ size_t gpart_bytes(const ctb_plan* plan, const ctb_time_groups* g, int n_out) {
 int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype, int layout,
                    int64_t stride, const int32_t* time_index, int64_t T, int transform,
                    const double* params, int n_params, int n_out, const ctb_time_groups* G,
-                   int64_t t_begin, int flush, const int32_t* day_of_year, double* out,
+                   int64_t t_begin, int flush, const int32_t* day_of_year, double* const* peer_out,
+                   int n_peer_out, double* out,
                    int64_t out_ld, void* workspace, size_t workspace_bytes, int variant, void* stream) {
   const char* fn = G ? "ctb_aggregate_grouped" : "ctb_aggregate";
   if (day_of_year && P && !P->has_gate) {
     ctb_set_error("%s: day_of_year given, but the plan was built without ctb_plan_opts.cell_gate", fn);
     return CTB_ERR_INVALID;
   }
+  if (n_peer_out < 0 || n_peer_out > CTB_MAX_PEERS || (n_peer_out > 0 && (!peer_out || G))) {
+    ctb_set_error("%s: peer_out takes 1..%d buffers and no time groups", fn, CTB_MAX_PEERS);
+    return CTB_ERR_INVALID;
+  }
+  if (n_peer_out > 0) out = peer_out[0];
   if (!P || !x0 || (!out && T > 0 && P->R > 0)) { ctb_set_error("%s: null argument", fn); return CTB_ERR_INVALID; }
   const int64_t n_cols = G ? G->n_groups : T;
   if (out_ld == 0) out_ld = n_cols;
@@ -251,6 +257,8 @@ int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype,
   a.n_tb = (int)((T + CTB_TB - 1) / CTB_TB);
   a.scratch_ld = T;
   a.doy = day_of_year; a.gate = P->d_gate;
+  a.n_peers = n_peer_out;
+  for (int p = 0; p < n_peer_out; ++p) a.peers[p] = peer_out[p];
   if (G) {
     a.tgroup = G->d_group; a.gk = G->gk; a.n_groups = G->n_groups; a.g_t_lo = G->d_t_lo; a.g_t_hi = G->d_t_hi;
     a.g_ntb = (int)((G->T + CTB_TB - 1) / CTB_TB); a.t_off = (int)t_begin; a.scratch_ld = G->T;
@@ -336,7 +344,7 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
                              double* out, int64_t out_ld, void* workspace,
                              size_t workspace_bytes, int variant, void* stream) {
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
-                        nullptr, 0, 1, nullptr, out, out_ld, workspace, workspace_bytes, variant, stream);
+                        nullptr, 0, 1, nullptr, nullptr, 0, out, out_ld, workspace, workspace_bytes, variant, stream);
 }
 
 // ------------------------------------------------------------ time groups ---
@@ -404,7 +412,8 @@ extern "C" int ctb_aggregate_grouped(const ctb_plan* P, const void* x0, const vo
                                      void* workspace, size_t workspace_bytes, int variant, void* stream) {
   if (!groups) { ctb_set_error("ctb_aggregate_grouped: null time groups"); return CTB_ERR_INVALID; }
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
-                        groups, t_begin, flush, nullptr, out, out_ld, workspace, workspace_bytes, variant, stream);
+                        groups, t_begin, flush, nullptr, nullptr, 0, out, out_ld, workspace, workspace_bytes, variant,
+                        stream);
 }
 
 extern "C" int ctb_aggregate_ex(const ctb_plan* P, const void* x0, const void* x1, int dtype, int layout,
@@ -415,6 +424,51 @@ extern "C" int ctb_aggregate_ex(const ctb_plan* P, const void* x0, const void* x
   const ctb_agg_opts none{};
   const ctb_agg_opts& o = opts ? *opts : none;
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
-                        o.groups, o.groups ? o.t_begin : 0, o.groups ? o.flush : 1, o.day_of_year, out, out_ld,
-                        workspace, workspace_bytes, variant, stream);
+                        o.groups, o.groups ? o.t_begin : 0, o.groups ? o.flush : 1, o.day_of_year, o.peer_out,
+                        o.n_peer_out, out, out_ld, workspace, workspace_bytes, variant, stream);
+}
+
+// ------------------------------------------------- peer-shared buffers (CUDA IPC) ---
+extern "C" int ctb_ipc_alloc(size_t bytes, int device, void** ptr, void* handle_out) {
+  if (!ptr || !handle_out || bytes == 0) { ctb_set_error("ctb_ipc_alloc: bad argument"); return CTB_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == CTB_IPC_HANDLE_BYTES, "IPC handle size");
+  CtbDeviceGuard guard(device);
+  CTB_CUDA(guard.err);
+  CTB_CUDA(cudaMalloc(ptr, bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    ctb_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return CTB_ERR_CUDA;
+  }
+  std::memcpy(handle_out, &h, sizeof h);
+  return CTB_OK;
+}
+
+extern "C" int ctb_ipc_open(const void* handle, int device, void** ptr) {
+  if (!ptr || !handle) { ctb_set_error("ctb_ipc_open: bad argument"); return CTB_ERR_INVALID; }
+  CtbDeviceGuard guard(device);
+  CTB_CUDA(guard.err);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof h);
+  CTB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return CTB_OK;
+}
+
+extern "C" int ctb_ipc_close(void* ptr, int device) {
+  if (!ptr) return CTB_OK;
+  CtbDeviceGuard guard(device);
+  CTB_CUDA(guard.err);
+  CTB_CUDA(cudaIpcCloseMemHandle(ptr));
+  return CTB_OK;
+}
+
+extern "C" int ctb_ipc_free(void* ptr, int device) {
+  if (!ptr) return CTB_OK;
+  CtbDeviceGuard guard(device);
+  CTB_CUDA(guard.err);
+  CTB_CUDA(cudaFree(ptr));
+  return CTB_OK;
 }

@@ -10,6 +10,9 @@ NVLink on GPUs, gloo in the CPU tests).  SURVEY.md section 8(e).
 * :func:`aggregate_shard_overlapped`          device level: the shard is aggregated in time pieces and
                                               the all_gather of piece k runs on a side stream while
                                               the kernel of piece k+1 runs
+* :class:`PeerOutput` / :func:`aggregate_shard_p2p`   the gather fused into the kernel: the epilogue
+                                              stores every result into all ranks' buffers over NVLink
+                                              peer memory (CUDA IPC), no collective
 * :func:`aggregate_time_sharded`              Dataset level (any leading dims)
 """
 from __future__ import annotations
@@ -19,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "shard_sizes", "all_gather_time", "aggregate_shard_overlapped",
-           "aggregate_time_sharded"]
+           "aggregate_time_sharded", "PeerOutput", "aggregate_shard_p2p"]
 
 
 def shard_sizes(T, world_size, align=32):
@@ -156,6 +159,86 @@ def aggregate_shard_overlapped(plan, x0, x1, stride, T, kind="identity", params=
     main.wait_stream(sb.side)
     return out, {"t0": sb.t0, "t1": sb.t0 + sb.tl, "pieces": len(sb.loc),
                  "bytes_received": int(8 * sb.M * (T - sb.tl))}
+
+
+class PeerOutput:
+    """``[n_out, R, T]`` float64 output buffers, one per rank of a single-node group, every one mapped
+    into every rank (CUDA IPC over NVLink peer memory).  :func:`aggregate_shard_p2p` makes the
+    aggregation kernel store each result to all of them: the final gather of a time-sharded job
+    happens inside the kernel's epilogue -- no collective, no staging copy."""
+
+    def __init__(self, plan, T, n_out=1, group=None):
+        import ctypes as C
+
+        from . import _native as N
+        self.group, self.plan, self.T, self.n_out = group, plan, T, n_out
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > N.MAX_PEERS:
+            raise ValueError("at most {} ranks".format(N.MAX_PEERS))
+        self.dev_index = plan.device.index or 0
+        self.shape = (n_out, plan.R, T)
+        nbytes = max(8, 8 * n_out * plan.R * T)
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * N.IPC_HANDLE_BYTES)()
+        N.check(N.lib().ctb_ipc_alloc(nbytes, self.dev_index, C.byref(ptr), handle))
+        self._own = ptr.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=plan.device)
+        allh = torch.empty((self.world, N.IPC_HANDLE_BYTES), dtype=torch.uint8, device=plan.device)
+        dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+        allh = allh.cpu().numpy()
+        self.ptrs, self._opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs.append(self._own)
+                continue
+            q = C.c_void_p()
+            hb = (C.c_ubyte * N.IPC_HANDLE_BYTES)(*allh[r].tolist())
+            N.check(N.lib().ctb_ipc_open(hb, self.dev_index, C.byref(q)))
+            self.ptrs.append(q.value)
+            self._opened.append(q.value)
+        # this rank's buffer as a tensor (a view: the memory belongs to this object)
+        self.out = _tensor_from_ptr(self._own, self.shape, plan.device, self)
+
+    def close(self):
+        from . import _native as N
+        torch.cuda.synchronize(self.plan.device)
+        if dist.is_initialized():
+            dist.barrier(self.group)       # nobody still writes into a buffer that is about to go
+        for q in self._opened:
+            N.lib().ctb_ipc_close(q, self.dev_index)
+        self._opened = []
+        if self._own:
+            N.lib().ctb_ipc_free(self._own, self.dev_index)
+            self._own = None
+
+
+def _tensor_from_ptr(ptr, shape, device, owner):
+    class _Mem:
+        def __init__(self):
+            self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                             "version": 3, "strides": None}
+            self.owner = owner
+    return torch.as_tensor(_Mem(), device=device)
+
+
+def aggregate_shard_p2p(plan, x0, x1, stride, T, peer_out, kind="identity", params=(), n_out=1):
+    """Time-sharded aggregation with the gather fused into the kernel: this rank aggregates days
+    ``shard_range(T)`` of ``x0`` and the kernel's epilogue stores every region-day to column ``t`` of
+    ALL ranks' ``[n_out, R, T]`` buffers (``peer_out``: a :class:`PeerOutput`).  After the
+    stream-ordered barrier that ends the call every rank's ``peer_out.out`` holds the full result."""
+    from . import _engine as E
+    from . import _native as N
+    world, rank = peer_out.world, peer_out.rank
+    t0, t1 = shard_range(T, world, rank)
+    n = t1 - t0
+    if n > 0:
+        a = x0[t0:t1]
+        b = x1[t0:t1] if x1 is not None else None
+        ptrs = [p + 8 * t0 for p in peer_out.ptrs]
+        E.aggregate_device(plan, a, b, N.LAYOUT_TIME_MAJOR, stride, None, n, kind, params, n_out,
+                           out=E._OffsetOut(peer_out.out, t0), out_ld=T, peer_ptrs=ptrs)
+    dist.barrier(peer_out.group)      # NCCL: stream-ordered after this rank's kernel, completes when all joined
+    return peer_out.out
 
 
 def aggregate_time_sharded(ds, variable, aggwt, agglev, weights, backup_aggwt="areawt", gather=True,

@@ -173,12 +173,18 @@ int ctb_aggregate(const ctb_plan* plan, const void* x0, const void* x1, int dtyp
  * fused form of multiplying the data by get_daily_growing_season_mask (utils.py:119-153), whose 0 and
  * NaN both leave the weighted sum untouched while the weight still counts in the denominator. */
 typedef struct ctb_time_groups ctb_time_groups;
+#define CTB_MAX_PEERS 8
 typedef struct ctb_agg_opts {
   const ctb_time_groups* groups;
   int64_t t_begin;
   int32_t flush;
-  int32_t reserved;
+  int32_t n_peer_out;               /* 0, or the number of output buffers the kernel writes (<= CTB_MAX_PEERS) */
   const int32_t* day_of_year;
+  double* const* peer_out;          /* HOST array of n_peer_out DEVICE pointers, each laid out like `out`
+                                       (this GPU's own buffer and peer-GPU buffers opened with ctb_ipc_open):
+                                       the kernel's epilogue stores every result to ALL of them -- the
+                                       all-gather of a time-sharded job fused into the aggregation kernel,
+                                       over NVLink peer memory.  `out` is ignored then.  Not with groups. */
 } ctb_agg_opts;
 int ctb_aggregate_ex(const ctb_plan* plan, const void* x0, const void* x1, int dtype, int layout,
                      int64_t stride, const int32_t* time_index, int64_t T, int transform,
@@ -186,6 +192,16 @@ int ctb_aggregate_ex(const ctb_plan* plan, const void* x0, const void* x1, int d
                      double* out, int64_t out_ld, void* workspace, size_t workspace_bytes, int variant,
                      void* stream);
 /* workspace of ctb_aggregate_ex: ctb_aggregate_workspace_bytes without groups, else the grouped one */
+
+/* ---- peer-shared output buffers (CUDA IPC) for the fused gather ------------ *
+ * ctb_ipc_alloc: cudaMalloc on `device` + an IPC handle (64 bytes) another process of the node opens
+ * with ctb_ipc_open (peer access enabled on demand); the owner frees with ctb_ipc_free, the others
+ * detach with ctb_ipc_close. */
+#define CTB_IPC_HANDLE_BYTES 64
+int ctb_ipc_alloc(size_t bytes, int device, void** ptr, void* handle_out);
+int ctb_ipc_open(const void* handle, int device, void** ptr);
+int ctb_ipc_close(void* ptr, int device);
+int ctb_ipc_free(void* ptr, int device);
 
 /* ---- pointwise helpers (materialising what the reference materialises) --- */
 /* out[j][i] = f_j(x0[i], x1[i]) for i < n; DEVICE pointers (transformations.py:69-89,189). */

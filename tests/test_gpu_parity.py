@@ -592,6 +592,27 @@ def test_several_weight_columns_quarter_degree():
         check(out["tas_" + c].values, ref, scale)
 
 
+def test_several_region_levels_and_weights_in_one_pass():
+    """SURVEY 8-f2: hierid + ISO x popwt + areawt from ONE pass over the data == four oracle passes;
+    the 180 ISO regions are far larger than a tile (split + fix-up), at 0.25 degree."""
+    lat, lon, df, tas, _, _ = _config(0.25, 24378, 3)
+    ds = Dataset({"tas": (("time", "lat", "lon"), torch.from_numpy(tas).cuda())},
+                 coords={"time": np.arange(3), "lat": lat, "lon": lon})
+    n0 = E.launch_count()
+    out = weighted_aggregate_grid_to_regions_multi(ds, "tas", ["popwt", "areawt"], ["hierid", "ISO"], df)
+    for lev in ("hierid", "ISO"):
+        for c in ("popwt", "areawt"):
+            ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, df, c, lev)
+            got = out["tas_{}_{}".format(c, lev)]
+            assert got.dims == rd and list(out[lev].values) == list(labels)
+            check(got.values, ref, scale)
+    # one streaming launch (+ the fix-up of the split regions), not four
+    out = weighted_aggregate_grid_to_regions_multi(ds, "tas", ["popwt", "areawt"], ["hierid", "ISO"], df)
+    n1 = E.launch_count()
+    out = weighted_aggregate_grid_to_regions_multi(ds, "tas", ["popwt", "areawt"], ["hierid", "ISO"], df)
+    assert E.launch_count() - n1 == 2
+
+
 def test_config5_slice_model_years_through_a_buffer_pool():
     """Config 5 (ensemble streaming): model-years from a pool of resident buffers through ONE plan and
     one reused output buffer, as bench.py --workload config5 does -- every model-year's output is
