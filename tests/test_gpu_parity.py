@@ -679,6 +679,26 @@ def test_plan_cache_sees_in_place_edits_of_the_weights_frame():
         np.nan_to_num(m1["tas_areawt"].values), np.nan_to_num(m2["tas_areawt"].values))
 
 
+def test_public_api_from_pinned_memory_pulls_and_returns_in_chunks():
+    """Pinned host source through the public API: the GPU pulls the referenced pieces (ctb_pull_pack) and
+    the result comes back in time chunks (ctb_copy_rows_to_host) while later chunks are pulled."""
+    lat, lon, df, tas, _, _ = _config(1.0, 3000, 330)
+    host = torch.empty(tas.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(torch.from_numpy(tas))
+    time = pd.date_range("2004-01-01", periods=330)             # crosses Feb 29: a lazy time take on top
+    ds = Dataset({"tas": (("time", "lat", "lon"), host.numpy())}, coords={"time": time, "lat": lat, "lon": lon})
+    ds1 = tas_poly(ds, 1, "t1")
+    n0 = E.TRANSFER_BYTES["d2h"]
+    out = weighted_aggregate_grid_to_regions(ds1, "t1", "popwt", "hierid", weights=df)
+    xt, tl = oracle.tas_poly(tas, time, 1)
+    ref, rd, labels, scale = oracle_agg(xt, ("time", "lat", "lon"), lat, lon, df, "popwt", "hierid")
+    assert out.t1.shape == ref.shape == (329, len(labels))
+    check(out.t1.values, ref, scale)
+    assert E.TRANSFER_BYTES["d2h"] - n0 == 8 * ref.size         # every result byte copied exactly once
+    forced = weighted_aggregate_grid_to_regions(ds1, "t1", "popwt", "hierid", weights=df, ingest="pack")
+    np.testing.assert_array_equal(forced.t1.values, out.t1.values)
+
+
 def test_back_to_back_host_calls_do_not_share_staging():
     """Two host-input calls with different data and keep_on_device=True: the second call packs into
     the pinned staging buffers the first call's last H2D copies may still be reading."""
