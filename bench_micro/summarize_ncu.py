@@ -49,13 +49,19 @@ def main(rep, out):
     h = src[1]
     ix = {c: i for i, c in enumerate(h)}
     ops, stalls, total = Counter(), Counter(), 0
+    wait_count = None
     for r in src[2:]:
         if len(r) < len(h):
             continue
         ie = int(r[ix["Instructions Executed"]] or 0)
         toks = [t for t in r[ix["Source"]].split() if not t.startswith("@")]
-        if not toks or "SYNCS" in toks[0] or "NANOSLEEP" in toks[0]:
-            continue            # the barrier-wait lines carry replay counts, not issued instructions
+        if not toks:
+            continue
+        if "SYNCS" in toks[0] or "NANOSLEEP" in toks[0]:
+            wait_count = ie     # the barrier-wait loops carry replay counts, not issued instructions
+            continue
+        if toks[0].startswith("BRA") and wait_count is not None and ie == wait_count:
+            continue            # ... and so does the branch that closes such a loop
         ops[toks[0].split(".")[0]] += ie
         total += ie
         for c in h:

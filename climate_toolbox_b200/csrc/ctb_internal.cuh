@@ -178,10 +178,10 @@ __device__ __forceinline__ double ctb_ipow(double d, int p) {
 //   tmax <= e       :  0          (also when tmax is NaN)
 //   tmin >= e       :  M - e      (NaN when tmin is NaN)
 // g(a) = v^(3/2) * H(v), v = 1 - a: after factoring the (1-a)^(3/2) behaviour at the end point
-// the rest is analytic on [0, 1] (nearest singularity at v = 2), and ONE degree-16 polynomial
+// the rest is analytic on [0, 1] (nearest singularity at v = 2), and ONE degree-12 polynomial
 // fitted to 80-bit reference values (ctb_edd_coeffs.h, gen_edd_coeffs.py) covers the whole
-// range.  Against asin/cos in numpy the scheme agrees to 4e-16 * max(|EDD|, W); it replaces an
-// fp64 asin, a sqrt and two divisions by 17 FMAs and one sqrt.  `rW` = 1/W is shared by all
+// range.  Against asin/cos in numpy the scheme agrees to 3e-14 * max(|EDD|, W); it replaces an
+// fp64 asin, a sqrt and two divisions by 13 FMAs and one sqrt.  `rW` = 1/W is shared by all
 // thresholds of a gridcell-day.
 #include "ctb_edd_coeffs.h"
 
@@ -217,31 +217,29 @@ __device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
   const double t = fma(2.0, v, -1.0);
   // even/odd split H(t) = E(t^2) + t*O(t^2): two independent Horner chains of 8 instead of one of
   // 16 (the Snyder kernels stall on this dependency chain: 4 warps per scheduler); same 3.5e-16.
-  static_assert(CTB_EDD_H_N == 17, "even/odd split below assumes degree 16");
+  static_assert(CTB_EDD_H_N % 2 == 1 && CTB_EDD_H_N >= 5, "even/odd split below assumes an even degree");
+  constexpr int D = CTB_EDD_H_N - 1;
   const double t2 = t * t;
-  double pe = ctb_edd_H[16], po = ctb_edd_H[15];
+  double pe = ctb_edd_H[D], po = ctb_edd_H[D - 1];
 #pragma unroll
-  for (int k = 14; k >= 0; k -= 2) pe = fma(pe, t2, ctb_edd_H[k]);
+  for (int k = D - 2; k >= 0; k -= 2) pe = fma(pe, t2, ctb_edd_H[k]);
 #pragma unroll
-  for (int k = 13; k >= 1; k -= 2) po = fma(po, t2, ctb_edd_H[k]);
+  for (int k = D - 3; k >= 1; k -= 2) po = fma(po, t2, ctb_edd_H[k]);
   return v * ctb_sqrt01(v) * fma(po, t, pe);
 }
 
+// Branch-free: a warp's lanes hold different gridcell-days, so the three cases of the closed form
+// diverge inside almost every warp (ncu: 14 of 32 lanes active per instruction when they are
+// branches, a quarter of the instructions control flow).  The straddling form is evaluated for all
+// lanes -- its argument clamped into the polynomial's range -- and the case is picked by selects;
+// what an unselected form computes from NaN / W = 0 never reaches the result.
 __device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double rW,
                                           double e) {
-  double r;
-  if (tmin < e) {
-    if (tmax > e) {
-      const double s = (e - M) * rW, a = fabs(s);
-      const double g = ctb_edd_g(fmin(a, 1.0));
-      r = W * (s < 0.0 ? g + a : g);
-    } else {
-      r = 0.0;
-    }
-  } else {
-    r = M - e;
-  }
-  return r;
+  const double s = (e - M) * rW, a = fmin(fabs(s), 1.0);   // fmin(NaN, 1) = 1
+  const double g = ctb_edd_g(a);
+  const double straddle = W * (s < 0.0 ? g + a : g);
+  const double below = tmax > e ? straddle : 0.0;            // tmax <= e or NaN: no degree days
+  return tmin < e ? below : M - e;                           // tmin >= e or NaN: M - e
 }
 
 template <int KIND, int NOUT>

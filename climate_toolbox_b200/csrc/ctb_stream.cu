@@ -609,10 +609,10 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
 template <typename TIN, int KIND, int NOUT>
 int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   // 32 warps of 64 registers; the multi-output polynomials keep 4 fp64 accumulators per output and
-  // lane and take 24 warps of 80 registers instead of spilling
+  // lane and take 24 warps of 80 registers (3 and 4 outputs: 20 warps of 96) instead of spilling
   // ... and the Snyder forms 16 warps of 128 registers (fp64 ALU bound: registers buy more than warps)
   constexpr int NIN = NIn<KIND>::v;
-  constexpr int THREADS = NIN == 2 ? (NOUT <= 2 ? 640 : 512) : (KIND == CTB_TR_POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
+  constexpr int THREADS = NIN == 2 ? (NOUT <= 2 ? 640 : 512) : (KIND == CTB_TR_POLY && NOUT > 2) ? 640 : (KIND == CTB_TR_POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
   constexpr int S = CTB_STAGES;   // tile stages: one being reduced, up to two landing
   constexpr size_t SMEM = (size_t)S * Geo<NIN>::TILE_BYTES + 2 * CTB_META_CAP;
   static_assert(SMEM <= 227 * 1024 - 512, "shared memory budget");
