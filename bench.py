@@ -555,7 +555,7 @@ def run_ours(args):
                                    s_steps, 3)
             ref, _ = aggregate_shard_overlapped(plan, x, None, ncell, T, kind, PARAMS[kind], n_out, pieces=1)
             torch.cuda.synchronize()
-            same = bool(torch.equal(torch.nan_to_num(po.out), torch.nan_to_num(ref)))
+            same = bool(torch.equal(torch.nan_to_num(po.gathered()), torch.nan_to_num(ref)))
             po.close()
         except Exception as ex:  # noqa: BLE001 -- IPC may be closed to the container: report, keep the NCCL numbers
             p2p_err, same = repr(ex)[:200], None

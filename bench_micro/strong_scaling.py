@@ -56,7 +56,7 @@ try:
     po = PeerOutput(plan, T)
     res["p2p_fused"] = timed(lambda: aggregate_shard_p2p(plan, x, None, x.shape[1], T, po))
     torch.cuda.synchronize()
-    ok = torch.equal(torch.nan_to_num(po.out), torch.nan_to_num(ref))
+    ok = torch.equal(torch.nan_to_num(po.gathered()), torch.nan_to_num(ref))
     res["p2p_equal_to_nccl_gather"] = float(ok)
     po.close()
 except Exception as ex:  # noqa: BLE001

@@ -95,6 +95,10 @@ class Plan:
     def den(self):
         return self._host_array("ctb_plan_den", self.R, np.float64, _dp)
 
+    def region_order(self):
+        """Position of every region along the bundle sequence (spatial order): a permutation of 0..R-1."""
+        return self._host_array("ctb_plan_region_order", self.R, np.int32, _ip)
+
     def algorithmic_bytes(self, T, n_in, elem_bytes, n_out):
         """T*(n_in*s_in*U + n_out*8*R) + 12*nnz."""
         i = self.info
@@ -321,7 +325,7 @@ def _workspace(plan, T, n_out, layout, variant, groups, workspace):
 
 
 def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out, variant, out, out_ld,
-            workspace, stream, groups=None, t_begin=0, flush=True, doy=None, peer_ptrs=None):
+            workspace, stream, groups=None, t_begin=0, flush=True, doy=None, peer_ptrs=None, peer_row=None):
     """Raw-pointer call of ctb_aggregate_ex (p0/p1: device or mapped-host addresses).  With ``groups``
     the result is [n_out, R, n_groups]; ``doy`` (int array, day of year of every day of the time axis)
     switches the growing-season gate of a plan built with ``cell_gate`` on; ``peer_ptrs`` (device
@@ -342,6 +346,7 @@ def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out
     if peer_ptrs:
         arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         o.peer_out, o.n_peer_out = arr, len(peer_ptrs)
+        o.peer_row = peer_row.data_ptr() if peer_row is not None else None
     rc = L.ctb_aggregate_ex(
         plan._h, C.c_void_p(p0), C.c_void_p(p1) if p1 else None, ctb_dtype, layout, int(stride),
         C.c_void_p(tix_d.data_ptr()) if tix_d is not None else None, int(T),
@@ -355,7 +360,7 @@ def _launch(plan, p0, p1, ctb_dtype, layout, stride, tix, T, kind, params, n_out
 
 def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", params=(), n_out=1,
                      variant=N.VARIANT_AUTO, out=None, out_ld=0, stream=None, workspace=None, groups=None,
-                     t_begin=0, flush=True, doy=None, peer_ptrs=None):
+                     t_begin=0, flush=True, doy=None, peer_ptrs=None, peer_row=None):
     """Launch the fused kernel on device-resident inputs.
 
     ``x0`` / ``x1``: contiguous CUDA tensors (f32/f64).  ``tix``: numpy int array of
@@ -371,7 +376,7 @@ def aggregate_device(plan, x0, x1, layout, stride, tix, T, kind="identity", para
         raise ValueError("the two inputs must agree in dtype and shape")
     return _launch(plan, x0.data_ptr(), x1.data_ptr() if x1 is not None else 0, _T2CTB[x0.dtype], layout,
                    stride, tix, T, kind, params, n_out, variant, out, out_ld, workspace, stream, groups,
-                   t_begin, flush, doy, peer_ptrs)
+                   t_begin, flush, doy, peer_ptrs, peer_row)
 
 
 def _all_pinned(xs):

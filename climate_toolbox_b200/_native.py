@@ -22,7 +22,7 @@ VARIANT_AUTO, VARIANT_STAGED, VARIANT_DIRECT = 0, 1, 2
 # every symbol include/ctb.h declares (tests check the .so exports each one)
 SYMBOLS = (
     "ctb_version", "ctb_last_error", "ctb_launch_count", "ctb_plan_build", "ctb_plan_free",
-    "ctb_plan_get_info", "ctb_plan_row_cells", "ctb_plan_den", "ctb_plan_row_weights",
+    "ctb_plan_get_info", "ctb_plan_row_cells", "ctb_plan_den", "ctb_plan_row_weights", "ctb_plan_region_order",
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
     "ctb_host_pack", "ctb_pull_pack", "ctb_copy_rows_to_host", "ctb_time_groups_create", "ctb_time_groups_free", "ctb_time_groups_count",
     "ctb_aggregate_grouped_workspace_bytes", "ctb_aggregate_grouped", "ctb_aggregate_ex",
@@ -38,7 +38,7 @@ class PlanOpts(C.Structure):
 
 class AggOpts(C.Structure):
     _fields_ = [("groups", C.c_void_p), ("t_begin", C.c_int64), ("flush", C.c_int32), ("n_peer_out", C.c_int32),
-                ("day_of_year", C.c_void_p), ("peer_out", C.POINTER(C.c_void_p))]
+                ("day_of_year", C.c_void_p), ("peer_out", C.POINTER(C.c_void_p)), ("peer_row", C.c_void_p)]
 
 
 MAX_PEERS = 8
@@ -96,7 +96,8 @@ def lib():
     L.ctb_plan_free.argtypes = [p]
     L.ctb_plan_get_info.restype = C.c_int
     L.ctb_plan_get_info.argtypes = [p, C.POINTER(PlanInfo)]
-    for name, ptr in (("ctb_plan_row_cells", ip), ("ctb_plan_den", dp), ("ctb_plan_row_weights", dp)):
+    for name, ptr in (("ctb_plan_row_cells", ip), ("ctb_plan_den", dp), ("ctb_plan_row_weights", dp),
+                      ("ctb_plan_region_order", ip)):
         getattr(L, name).restype = C.c_int
         getattr(L, name).argtypes = [p, ptr]
     L.ctb_aggregate_workspace_bytes.restype = C.c_size_t

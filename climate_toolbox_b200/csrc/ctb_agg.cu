@@ -54,7 +54,12 @@ __global__ void agg_fixup_kernel(const AggArgs a, int n_out) {
       for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < a.T; t += gridDim.y * blockDim.x) {
         double s = 0.0;
         for (int q = s0; q < s1; ++q) s += a.scratch[((size_t)j * a.n_scratch + q) * a.scratch_ld + t];
-        a.out[((size_t)j * a.R + r) * a.out_ld + t] = s / d;
+        if (a.n_peers == 0) {
+          a.out[((size_t)j * a.R + r) * a.out_ld + t] = s / d;
+        } else {
+          const int row = a.peer_row ? a.peer_row[r] : r;
+          for (int p = 0; p < a.n_peers; ++p) a.peers[p][((size_t)j * a.R + row) * a.out_ld + t] = s / d;
+        }
       }
     } else {
       for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < a.n_groups; g += gridDim.y * blockDim.x) {
@@ -190,7 +195,7 @@ int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype,
                    int64_t stride, const int32_t* time_index, int64_t T, int transform,
                    const double* params, int n_params, int n_out, const ctb_time_groups* G,
                    int64_t t_begin, int flush, const int32_t* day_of_year, double* const* peer_out,
-                   int n_peer_out, double* out,
+                   int n_peer_out, const int32_t* peer_row, double* out,
                    int64_t out_ld, void* workspace, size_t workspace_bytes, int variant, void* stream) {
   const char* fn = G ? "ctb_aggregate_grouped" : "ctb_aggregate";
   if (day_of_year && P && !P->has_gate) {
@@ -258,6 +263,7 @@ int aggregate_impl(const ctb_plan* P, const void* x0, const void* x1, int dtype,
   a.scratch_ld = T;
   a.doy = day_of_year; a.gate = P->d_gate;
   a.n_peers = n_peer_out;
+  a.peer_row = n_peer_out ? peer_row : nullptr;
   for (int p = 0; p < n_peer_out; ++p) a.peers[p] = peer_out[p];
   if (G) {
     a.tgroup = G->d_group; a.gk = G->gk; a.n_groups = G->n_groups; a.g_t_lo = G->d_t_lo; a.g_t_hi = G->d_t_hi;
@@ -344,7 +350,8 @@ extern "C" int ctb_aggregate(const ctb_plan* P, const void* x0, const void* x1, 
                              double* out, int64_t out_ld, void* workspace,
                              size_t workspace_bytes, int variant, void* stream) {
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
-                        nullptr, 0, 1, nullptr, nullptr, 0, out, out_ld, workspace, workspace_bytes, variant, stream);
+                        nullptr, 0, 1, nullptr, nullptr, 0, nullptr, out, out_ld, workspace, workspace_bytes, variant,
+                        stream);
 }
 
 // ------------------------------------------------------------ time groups ---
@@ -412,8 +419,8 @@ extern "C" int ctb_aggregate_grouped(const ctb_plan* P, const void* x0, const vo
                                      void* workspace, size_t workspace_bytes, int variant, void* stream) {
   if (!groups) { ctb_set_error("ctb_aggregate_grouped: null time groups"); return CTB_ERR_INVALID; }
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
-                        groups, t_begin, flush, nullptr, nullptr, 0, out, out_ld, workspace, workspace_bytes, variant,
-                        stream);
+                        groups, t_begin, flush, nullptr, nullptr, 0, nullptr, out, out_ld, workspace, workspace_bytes,
+                        variant, stream);
 }
 
 extern "C" int ctb_aggregate_ex(const ctb_plan* P, const void* x0, const void* x1, int dtype, int layout,
@@ -425,7 +432,7 @@ extern "C" int ctb_aggregate_ex(const ctb_plan* P, const void* x0, const void* x
   const ctb_agg_opts& o = opts ? *opts : none;
   return aggregate_impl(P, x0, x1, dtype, layout, stride, time_index, T, transform, params, n_params, n_out,
                         o.groups, o.groups ? o.t_begin : 0, o.groups ? o.flush : 1, o.day_of_year, o.peer_out,
-                        o.n_peer_out, out, out_ld, workspace, workspace_bytes, variant, stream);
+                        o.n_peer_out, o.peer_row, out, out_ld, workspace, workspace_bytes, variant, stream);
 }
 
 // ------------------------------------------------- peer-shared buffers (CUDA IPC) ---

@@ -139,6 +139,7 @@ struct ctb_plan {
   std::vector<int32_t> h_row_cell;
   std::vector<double> h_row_w;
   std::vector<double> h_den;
+  std::vector<int32_t> h_region_pos;   // position of every region along the bundle sequence (spatial order)
   ctb_plan_info info{};
 };
 
@@ -312,9 +313,11 @@ struct AggArgs {
   // growing-season gate: day of year of day t_off + t; NULL = no gate.  gate: per CSR entry (direct kernel)
   const int32_t* doy;
   const uint32_t* gate;
-  // fused gather: n_peers > 0 => every result is stored to peers[0..n_peers) (own + NVLink peer buffers)
+  // fused gather: n_peers > 0 => every result is stored to peers[0..n_peers) (own + NVLink peer buffers),
+  // region r in row peer_row[r] (NULL: r)
   int n_peers;
   double* peers[CTB_MAX_PEERS];
+  const int32_t* peer_row;
   const int32_t *row_ptr, *col;
   const double* w;
   const int32_t *split_region, *split_slot_ptr;
@@ -345,10 +348,14 @@ __device__ __forceinline__ void ctb_emit(const AggArgs& a, int target, double rd
     if (target >= 0) {
 #pragma unroll
       for (int j = 0; j < NOUT; ++j) {   // written once: leave L2 to the input
-        const size_t idx = ((size_t)j * a.R + target) * a.out_ld + t;
         const double val = v[j] * rden;
-        if (a.n_peers == 0) __stcs(&a.out[idx], val);
-        else for (int p = 0; p < a.n_peers; ++p) __stcs(&a.peers[p][idx], val);
+        if (a.n_peers == 0) {
+          __stcs(&a.out[((size_t)j * a.R + target) * a.out_ld + t], val);
+        } else {
+          const int row = a.peer_row ? __ldg(a.peer_row + target) : target;
+          const size_t idx = ((size_t)j * a.R + row) * a.out_ld + t;
+          for (int p = 0; p < a.n_peers; ++p) __stcs(&a.peers[p][idx], val);
+        }
       }
     } else {
       const int slot_o = ~target;

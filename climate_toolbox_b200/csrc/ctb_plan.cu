@@ -554,6 +554,14 @@ static int plan_build_impl(const double* grid_lat, int32_t nlat, const int32_t* 
   }
   std::stable_sort(regs.begin(), regs.end(),
                    [](const Region& a, const Region& b) { return a.hkey < b.hkey; });
+  // the bundle sequence as a region permutation (regions without kept rows last): rows written in this
+  // order keep the stores of one CTA inside a few pages (the fused peer-memory gather needs that)
+  P->h_region_pos.assign(R, 0);
+  {
+    int32_t pos = 0;
+    for (const Region& g : regs) P->h_region_pos[g.r] = pos++;
+    for (int32_t r : empty_regions) P->h_region_pos[r] = pos++;
+  }
 
   const int64_t npiece_grid = (plan_ncell + CTB_PIECE - 1) / CTB_PIECE;
   std::vector<int32_t> stamp(npiece_grid, -1);   // piece -> bundle generation that holds it
@@ -726,6 +734,12 @@ extern "C" int ctb_plan_row_cells(const ctb_plan* plan, int32_t* out) {
 extern "C" int ctb_plan_den(const ctb_plan* plan, double* out) {
   if (!plan || !out) { ctb_set_error("null argument"); return CTB_ERR_INVALID; }
   std::memcpy(out, plan->h_den.data(), plan->h_den.size() * sizeof(double));
+  return CTB_OK;
+}
+
+extern "C" int ctb_plan_region_order(const ctb_plan* plan, int32_t* out) {
+  if (!plan || !out) { ctb_set_error("null argument"); return CTB_ERR_INVALID; }
+  std::memcpy(out, plan->h_region_pos.data(), plan->h_region_pos.size() * sizeof(int32_t));
   return CTB_OK;
 }
 

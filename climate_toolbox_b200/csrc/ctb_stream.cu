@@ -575,14 +575,16 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
           if (target >= 0) {
 #pragma unroll
             for (int j = 0; j < NOUT; ++j) {   // written once: leave L2 to the input
-              const size_t idx = ((size_t)j * a.R + target) * a.out_ld;
               const double val = v[j] * rden;
               if (a.n_peers == 0) {
-                __stcs(out_t + idx, val);
+                __stcs(out_t + ((size_t)j * a.R + target) * a.out_ld, val);
               } else {
                 // fused gather: the tile's 256 bytes go to this GPU's buffer and, over NVLink, to
-                // every peer's -- no collective, no staging copy after the kernel
-                for (int p = 0; p < a.n_peers; ++p) __stcs(a.peers[p] + t + idx, val);
+                // every peer's -- no collective, no staging copy after the kernel.  Rows in bundle
+                // order (peer_row): the CTA's stores stay inside a few pages per peer
+                const int row = a.peer_row ? __ldg(a.peer_row + target) : target;
+                const size_t idx = ((size_t)j * a.R + row) * a.out_ld + t;
+                for (int p = 0; p < a.n_peers; ++p) __stcs(a.peers[p] + idx, val);
               }
             }
           } else {

@@ -141,6 +141,9 @@ int ctb_plan_get_info(const ctb_plan* plan, ctb_plan_info* info);
 int ctb_plan_row_cells(const ctb_plan* plan, int32_t* cells_out /*[n_rows]*/);
 int ctb_plan_den(const ctb_plan* plan, double* den_out /*[n_regions]*/);
 int ctb_plan_row_weights(const ctb_plan* plan, double* w_out /*[n_rows]*/);
+/* HOST output: position of every region along the plan's bundle sequence (a permutation of 0..R-1 that
+ * keeps spatial neighbours together); the row order ctb_agg_opts.peer_row is meant for */
+int ctb_plan_region_order(const ctb_plan* plan, int32_t* pos_out /*[n_regions]*/);
 
 /* ---- K1+K2(+K3): fused stage + gather + segmented weighted sum ----------- *
  * Replaces aggregations.py:75-82 (and the gather of :27) with the transform of
@@ -185,6 +188,10 @@ typedef struct ctb_agg_opts {
                                        the kernel's epilogue stores every result to ALL of them -- the
                                        all-gather of a time-sharded job fused into the aggregation kernel,
                                        over NVLink peer memory.  `out` is ignored then.  Not with groups. */
+  const int32_t* peer_row;          /* DEVICE int32[n_regions], nullable: row of every region in the peer
+                                       buffers.  ctb_plan_region_order keeps one CTA's stores inside a few
+                                       pages: with sorted-label rows a CTA touches ~28 pages per peer and tile,
+                                       and 8 peers overflow the TLB (measured: 3.2 ms instead of 0.4) */
 } ctb_agg_opts;
 int ctb_aggregate_ex(const ctb_plan* plan, const void* x0, const void* x1, int dtype, int layout,
                      int64_t stride, const int32_t* time_index, int64_t T, int transform,

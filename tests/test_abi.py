@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_struct_layouts_match_header(built):
     # sizes follow from the field lists in include/ctb.h
     assert ctypes.sizeof(_native.PlanOpts) == 32 + 8            # 8 x int32 + the cell_gate pointer
-    assert ctypes.sizeof(_native.AggOpts) == 8 + 8 + 4 + 4 + 8 + 8   # groups, t_begin, flush, n_peer_out, day_of_year, peer_out
+    assert ctypes.sizeof(_native.AggOpts) == 8 + 8 + 4 + 4 + 8 + 8 + 8   # groups, t_begin, flush, n_peer_out, day_of_year, peer_out, peer_row
     assert _native.gate_word(0, 511, 0) == _native.GATE_ALWAYS
     assert ctypes.sizeof(_native.PlanInfo) == 4 * 8 + 2 * 4 + 2 * 8 + 8 * 4 + 2 * 8
 
