@@ -176,8 +176,10 @@ def test_stacked_weight_columns_for_one_pass_multi_weight():
     df = synthetic.weights_table(5.0, 40, seed=3).copy()
     df.loc[df.index[::11], "hierid"] = np.nan
     cols = ["popwt", "cropwt"]
-    st, labels, present = _stack_weight_columns(df, cols, "hierid", "areawt")
+    st, labels, combos, present = _stack_weight_columns(df, cols, ["hierid"], "areawt")
+    labels = labels["hierid"]
     R = len(labels)
+    assert [(c[0], c[1], c[2]) for c in combos] == [("hierid", "popwt", 0), ("hierid", "cropwt", R)]
     assert len(st) == 2 * len(df) and list(labels) == sorted(set(df.hierid.dropna()))
     assert np.isnan(st["_lev"].values).sum() == 2 * df.hierid.isna().sum()
     np.testing.assert_array_equal(present, np.arange(2 * R))
@@ -186,6 +188,14 @@ def test_stacked_weight_columns_for_one_pass_multi_weight():
     for k, c in enumerate(cols):
         ref = oracle.weighted_aggregate_grid_to_regions(x, ("time", "lat", "lon"), lat, lon, df, c, "hierid")[0]
         np.testing.assert_allclose(got[:, k * R:(k + 1) * R], ref, rtol=1e-13, equal_nan=True)
+    # several region levels: every (level, weight) pair gets its own block of virtual regions
+    st2, labels2, combos2, present2 = _stack_weight_columns(df, ["popwt"], ["hierid", "ISO"], "areawt")
+    R2 = len(labels2["ISO"])
+    assert [(c[0], c[2], c[3]) for c in combos2] == [("hierid", 0, R), ("ISO", R, R2)] and len(st2) == 2 * len(df)
+    got2 = oracle.weighted_aggregate_grid_to_regions(x, ("time", "lat", "lon"), lat, lon, st2, "_w", "_lev", "_bk")[0]
+    ref_iso = oracle.weighted_aggregate_grid_to_regions(x, ("time", "lat", "lon"), lat, lon, df, "popwt", "ISO")[0]
+    sel = np.flatnonzero((present2 >= R) & (present2 < R + R2))
+    np.testing.assert_allclose(got2[:, sel], ref_iso, rtol=1e-13, equal_nan=True)
 
 
 # ----------------------------------------------------------------------------
