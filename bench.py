@@ -235,6 +235,10 @@ class Bench:
             raise SystemExit("--gpus {} needs torchrun with {} ranks".format(args.gpus, args.gpus))
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.cpus = None
+        if self.world > 1:   # host buffers on the GPU's own socket (the e2e leg pulls them over PCIe)
+            from climate_toolbox_b200.parallel import bind_to_gpu_numa_node
+            self.cpus = bind_to_gpu_numa_node(self.local)
         if self.world > 1:   # ranks share the host cores for the e2e packing
             os.environ.setdefault("CTB_PACK_THREADS", str(max(1, (3 * (os.cpu_count() or 1)) // (4 * self.world))))
             dist.init_process_group("nccl", device_id=self.dev)
@@ -507,8 +511,9 @@ def run_ours(args):
                "warmup_calls": m["warmup_calls"], "steps": e2e_steps,
                "pinned_result_blocks_allocated": int(sum(E._RESULT_OUT.values())),
                "api": "weighted_aggregate_grid_to_regions(ds[numpy over pinned host memory], ...) -> Dataset[numpy]: "
-                      "host packing of the referenced gridcells + pinned chunked H2D + fused kernel + pinned D2H",
-               "checksum": m["checksum"]}
+                      "GPU pull of the referenced gridcells from pinned host memory (ctb_pull_pack) in time chunks + fused kernel + chunked 2-D D2H into pinned memory",
+               "checksum": m["checksum"],
+               "rank0_cpu_affinity": (len(B.cpus) if B.cpus else None)}
         if kind == "identity":
             # the step after the path fused in (annual sums): the result block shrinks 365x
             my = measure(ds, names, max(2, e2e_steps // 2), min_warm=2, warm_s=0.5, time_groups=365)

@@ -21,8 +21,30 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_sizes", "all_gather_time", "aggregate_shard_overlapped",
+__all__ = ["bind_to_gpu_numa_node", "shard_range", "shard_sizes", "all_gather_time", "aggregate_shard_overlapped",
            "aggregate_time_sharded", "PeerOutput", "aggregate_shard_p2p"]
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPU cores next to its GPU (NVML's affinity mask) -- call it BEFORE the
+    host arrays are allocated: pinned pages then live on the socket whose PCIe root the GPU hangs off,
+    and the GPU-side ingest (``ctb_pull_pack``) of eight ranks does not cross the inter-socket link.
+    Returns the core list, or None when NVML / the scheduler call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:  # noqa: BLE001 -- best effort: no NVML, no permission, not Linux
+        pass
+    return None
 
 
 def shard_sizes(T, world_size, align=32):
