@@ -149,7 +149,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 // 16-byte asynchronous copy global -> shared, L2 only (SASS: LDGSTS.E.BYPASS.128)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+#ifdef CTB_CP_L2
+#define CTB_STR2(x) #x
+#define CTB_STR(x) CTB_STR2(x)
+  asm volatile("cp.async.cg.shared.global.L2::" CTB_STR(CTB_CP_L2) "B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 // the executing thread's earlier cp.async copies arrive on the mbarrier when they have landed
 __device__ __forceinline__ void cp_async_arrive_a(uint32_t bar) {
