@@ -1,4 +1,4 @@
-"""A few launches of the config-2 kernel (for ncu): python bench_micro/one_launch.py [workload] [n]"""
+"""A few launches of the config-2 kernel (for ncu): python bench_micro/one_launch.py [identity|poly|edd|packed] [n]"""
 import os
 import sys
 
@@ -24,7 +24,16 @@ elif kind == "edd":
     x1 = x + (3.0 * torch.randn(x.shape, generator=g, device=dev, dtype=torch.float32)).abs()
     x = x - (3.0 * torch.randn(x.shape, generator=g, device=dev, dtype=torch.float32)).abs()
     params, n_out, aggwt, sb = (283.15, 303.15), 2, "cropwt", 8
-plan = E.get_plan(E.GridSpec(lat, lon), df, aggwt, "hierid", device=dev, stage_bytes=sb)
+packed = kind == "packed"
+if packed:
+    kind = "identity"
+plan = E.get_plan(E.GridSpec(lat, lon), df, aggwt, "hierid", device=dev, stage_bytes=sb, compact=packed)
+if packed:   # compact the archive on the device once, then aggregate the packed planes
+    import ctypes as C
+    xp = torch.empty((T, plan.info["n_packed_cells"]), dtype=torch.float32, device=dev)
+    N.check(N.lib().ctb_pull_pack(plan._h, C.c_void_p(x.data_ptr()), N.F32, x.shape[1], None, 0, T,
+                                  C.c_void_p(xp.data_ptr()), E._stream_ptr(dev)))
+    x = xp
 out = torch.empty((n_out, plan.R, T), dtype=torch.float64, device=dev)
 for _ in range(n):
     E.aggregate_device(plan, x, x1, N.LAYOUT_TIME_MAJOR, x.shape[1], None, T, kind, params, n_out, out=out)

@@ -161,6 +161,10 @@ struct CtbTr {
   int ip[4];    // integer powers (POLY)
 };
 
+// internal transform kind: CTB_TR_POLY whose orders are 1..n_out (checked on the host by the
+// launcher), so that the kernel carries one running product and no order tests (config 3)
+constexpr int CTB_TR_POLY_SEQ = 16;
+
 __device__ __forceinline__ double ctb_ipow(double d, int p) {
   // integer power by squaring; p is warp-uniform
   double r = 1.0, b = d;
@@ -247,6 +251,14 @@ template <int KIND, int NOUT>
 __device__ __forceinline__ void ctb_apply(const CtbTr& P, double x0, double x1, double (&f)[NOUT]) {
   if constexpr (KIND == CTB_TR_IDENTITY) {
     f[0] = x0;
+  } else if constexpr (KIND == CTB_TR_POLY_SEQ) {
+    const double d = x0 - P.a[0];
+    double p = d;
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) {
+      f[j] = p;
+      p *= d;
+    }
   } else if constexpr (KIND == CTB_TR_POLY) {
     const double d = x0 - P.a[0];
     bool chain = true;

@@ -265,6 +265,9 @@ __device__ __forceinline__ void reduce_region(const CtbTr& tr, uint32_t tile_a, 
 // min / max of the raw bit patterns (one ALU instruction per value) tells whether the region-tile
 // saw anything else -- zero, a denormal, a negative number, an infinity or a NaN -- and then the
 // caller reduces it again with the exact loops.  Returns false in that case.
+#ifndef CTB_POLY34_UNROLL
+#define CTB_POLY34_UNROLL 2
+#endif
 template <int KIND, int NOUT, bool GATE>
 __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
                                                     int lane, const int (&doy)[4], double (&v)[NOUT]) {
@@ -278,7 +281,8 @@ __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t ti
   auto widen = [](uint32_t b) {
     return __longlong_as_double((long long)((unsigned long long)b * 0x20000000ull + 0x3800000000000000ull));
   };
-#pragma unroll 2
+  constexpr int UNR = NOUT > 2 ? CTB_POLY34_UNROLL : 2;
+#pragma unroll(UNR)
   for (int q = 0; q < nq; ++q, ent_a += 4 * (uint32_t)sizeof(CtbEnt)) {
     const uint4 m = lds_u4(ent_a);
     const double w = __hiloint2double((int)m.y, (int)m.x);
@@ -614,13 +618,17 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
   }
 }
 
+#ifndef CTB_POLY34_THREADS
+#define CTB_POLY34_THREADS 640
+#endif
 template <typename TIN, int KIND, int NOUT>
 int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   // 32 warps of 64 registers; the multi-output polynomials keep 4 fp64 accumulators per output and
   // lane and take 24 warps of 80 registers (3 and 4 outputs: 20 warps of 96) instead of spilling
   // ... and the Snyder forms 16 warps of 128 registers (fp64 ALU bound: registers buy more than warps)
   constexpr int NIN = NIn<KIND>::v;
-  constexpr int THREADS = NIN == 2 ? (NOUT <= 2 ? 640 : 512) : (KIND == CTB_TR_POLY && NOUT > 2) ? 640 : (KIND == CTB_TR_POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
+  constexpr bool POLY = KIND == CTB_TR_POLY || KIND == CTB_TR_POLY_SEQ;
+  constexpr int THREADS = NIN == 2 ? (NOUT <= 2 ? 640 : 512) : (POLY && NOUT > 2) ? CTB_POLY34_THREADS : (POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
   constexpr int S = CTB_STAGES;   // tile stages: one being reduced, up to two landing
   constexpr size_t SMEM = (size_t)S * Geo<NIN>::TILE_BYTES + 2 * CTB_META_CAP;
   static_assert(SMEM <= 227 * 1024 - 512, "shared memory budget");
@@ -672,7 +680,12 @@ int launch_kind(const ctb_plan* P, const AggArgs& a, int kind, int n_out, cudaSt
     case 3: return launch<TIN, K, 3>(P, a, st);              \
     case 4: return launch<TIN, K, 4>(P, a, st);              \
   }
-  if (kind == CTB_TR_POLY) { CTB_NOUT_SWITCH(CTB_TR_POLY) }
+  if (kind == CTB_TR_POLY) {
+    bool seq = true;   // orders 1..n_out (tas_poly's usual call): no order tests in the kernel
+    for (int j = 0; j < n_out; ++j) seq = seq && a.tr.ip[j] == j + 1;
+    if (seq) { CTB_NOUT_SWITCH(CTB_TR_POLY_SEQ) }
+    CTB_NOUT_SWITCH(CTB_TR_POLY)
+  }
   if (kind == CTB_TR_EDD) { CTB_NOUT_SWITCH(CTB_TR_EDD) }
   if (kind == CTB_TR_GDD) { CTB_NOUT_SWITCH(CTB_TR_GDD) }
 #undef CTB_NOUT_SWITCH
