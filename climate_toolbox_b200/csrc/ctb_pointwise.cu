@@ -117,3 +117,62 @@ extern "C" int ctb_copy_rows_to_host(void* dst, size_t dst_pitch, const void* sr
                              (cudaStream_t)stream));
   return CTB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Push a column block of a row-major [n_rows][ld] fp64 array to the same place in every peer buffer
+// (multi-GPU strong scaling: each rank owns days [t0, t0 + n_cols) of the [R][T] result).  A warp
+// takes a row: lane l reads columns l, l+32, ... once (up to 8 per pass, independent loads) and
+// stores them to each peer -- coalesced row pieces instead of the 256-byte pieces per region and
+// tile the fused epilogue scatters.
+namespace {
+struct PushPeers { double* p[CTB_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256) push_rows_kernel(const double* __restrict__ src, int64_t ld, int64_t t0,
+                                                         int n_cols, int64_t n_rows, int n_peers, PushPeers peers) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const int64_t base = r * ld + t0;
+    for (int c0 = 0; c0 < n_cols; c0 += 256) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k * 32 + lane;
+        v[k] = c < n_cols ? __ldcs(src + base + c) : 0.0;
+      }
+      for (int p = 0; p < n_peers; ++p) {
+        double* const dst = peers.p[p] + base;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = c0 + k * 32 + lane;
+          if (c < n_cols) dst[c] = v[k];
+        }
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int ctb_push_rows(const double* src, int64_t ld, int64_t t0, int64_t n_cols, int64_t n_rows, int n_peers,
+                             double* const* peers, void* stream) {
+  if (n_peers < 0 || n_peers > CTB_MAX_PEERS || ld < 0 || t0 < 0 || n_cols < 0 || n_rows < 0 || t0 + n_cols > ld ||
+      n_cols >= (1ll << 31)) {
+    ctb_set_error("ctb_push_rows: bad shape (ld=%lld t0=%lld n_cols=%lld n_rows=%lld n_peers=%d)", (long long)ld,
+                  (long long)t0, (long long)n_cols, (long long)n_rows, n_peers);
+    return CTB_ERR_INVALID;
+  }
+  if (n_cols == 0 || n_rows == 0 || n_peers == 0) return CTB_OK;
+  if (!src || !peers) { ctb_set_error("ctb_push_rows: null argument"); return CTB_ERR_INVALID; }
+  PushPeers pp{};
+  int n = 0;
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peers[p]) { ctb_set_error("ctb_push_rows: null peer pointer %d", p); return CTB_ERR_INVALID; }
+    if (peers[p] != src) pp.p[n++] = peers[p];
+  }
+  if (n == 0) return CTB_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((n_rows + 7) / 8, 148 * 8);
+  push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, t0, (int)n_cols, n_rows, n, pp);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}

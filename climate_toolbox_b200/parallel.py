@@ -227,9 +227,29 @@ class PeerOutput:
         self.row_of_region = torch.as_tensor(pos, device=plan.device)                 # region -> row
         self._region_rows = self.row_of_region.to(torch.int64)
 
+        self.rows = "bundle"          # row order of ``raw`` after the last call: "bundle" (fused) or "region" (push)
+
     def gathered(self):
-        """The full result in the reference's region order ``[n_out, R, T]`` (one device gather)."""
+        """The full result in the reference's region order ``[n_out, R, T]`` (one device gather after the
+        fused form; the buffer itself after the push form)."""
+        if self.rows == "region":
+            return self.raw
         return self.raw.index_select(1, self._region_rows)
+
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.plan.device)
+        return self._side
+
+    def push(self, t0, n):
+        """Copy columns ``[t0, t0 + n)`` of this rank's buffer into every peer's (``ctb_push_rows``)."""
+        import ctypes as C
+
+        from . import _engine as E
+        from . import _native as N
+        arr = (C.c_void_p * self.world)(*self.ptrs)
+        N.check(N.lib().ctb_push_rows(C.c_void_p(self._own), self.T, t0, n, self.n_out * self.plan.R, self.world,
+                                      arr, E._stream_ptr(self.plan.device)))
 
     def close(self):
         from . import _native as N
@@ -253,26 +273,63 @@ def _tensor_from_ptr(ptr, shape, device, owner):
     return torch.as_tensor(_Mem(), device=device)
 
 
-def aggregate_shard_p2p(plan, x0, x1, stride, T, peer_out, kind="identity", params=(), n_out=1, gathered=True):
-    """Time-sharded aggregation with the gather fused into the kernel: this rank aggregates days
-    ``shard_range(T)`` of ``x0`` and the kernel's epilogue stores every region-day to column ``t`` of
-    ALL ranks' ``[n_out, R, T]`` buffers (``peer_out``: a :class:`PeerOutput`).  After the
-    stream-ordered barrier that ends the call every rank holds the full result: ``peer_out.raw`` with
-    the regions in the plan's bundle order (``peer_out.row_of_region``), returned in the reference's
-    label order after one device gather when ``gathered``."""
+def aggregate_shard_p2p(plan, x0, x1, stride, T, peer_out, kind="identity", params=(), n_out=1, gathered=True,
+                        mode="auto", pieces=2):
+    """Time-sharded aggregation whose gather needs no collective: this rank aggregates days
+    ``shard_range(T)`` of ``x0`` and every rank ends with the full ``[n_out, R, T]`` result in its own
+    peer-mapped buffer (``peer_out``: a :class:`PeerOutput`).
+
+    ``mode="fused"``: the kernel's epilogue stores every region-day to column ``t`` of ALL ranks'
+    buffers (rows in the plan's bundle order, ``peer_out.row_of_region``; best for 2 ranks).
+    ``mode="push"``: the kernel writes this rank's own buffer and one copy kernel
+    (``ctb_push_rows``) sends the finished column block to every peer as coalesced row pieces (best
+    from 4 ranks: the fused form's 256-byte pieces per region and tile are too scattered for many
+    destinations; in ``pieces`` time pieces, the push of one under the kernel of the next).
+    ``"auto"`` picks by the group size.  A stream-ordered barrier ends the call;
+    the result comes back in the reference's label order when ``gathered`` (else ``peer_out.raw``
+    in the order ``peer_out.rows`` names)."""
     from . import _engine as E
     from . import _native as N
     world, rank = peer_out.world, peer_out.rank
+    if mode == "auto":
+        mode = "fused" if world <= 2 else "push"
+    if mode not in ("fused", "push"):
+        raise ValueError("mode must be 'auto', 'fused' or 'push'")
     t0, t1 = shard_range(T, world, rank)
     n = t1 - t0
     if n > 0:
         a = x0[t0:t1]
         b = x1[t0:t1] if x1 is not None else None
-        ptrs = [p + 8 * t0 for p in peer_out.ptrs]
-        E.aggregate_device(plan, a, b, N.LAYOUT_TIME_MAJOR, stride, None, n, kind, params, n_out,
-                           out=E._OffsetOut(peer_out.raw, t0), out_ld=T, peer_ptrs=ptrs,
-                           peer_row=peer_out.row_of_region)
-    dist.barrier(peer_out.group)      # NCCL: stream-ordered after this rank's kernel, completes when all joined
+        if mode == "fused":
+            ptrs = [p + 8 * t0 for p in peer_out.ptrs]
+            E.aggregate_device(plan, a, b, N.LAYOUT_TIME_MAJOR, stride, None, n, kind, params, n_out,
+                               out=E._OffsetOut(peer_out.raw, t0), out_ld=T, peer_ptrs=ptrs,
+                               peer_row=peer_out.row_of_region)
+        else:
+            # in `pieces` time pieces (multiples of the kernel's 32-day tiles): the push of piece k runs
+            # on a side stream under the kernel of piece k+1
+            step = max(32, -(-n // max(1, pieces) // 32) * 32)
+            main = torch.cuda.current_stream(plan.device)
+            side = peer_out.side_stream()
+            for p0 in range(0, n, step):
+                m = min(step, n - p0)
+                E.aggregate_device(plan, a[p0:p0 + m], None if b is None else b[p0:p0 + m], N.LAYOUT_TIME_MAJOR,
+                                   stride, None, m, kind, params, n_out, out=E._OffsetOut(peer_out.raw, t0 + p0),
+                                   out_ld=T)
+                if p0 + m < n:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        peer_out.push(t0 + p0, m)
+                else:
+                    peer_out.push(t0 + p0, m)
+            if n > step:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
+    peer_out.rows = "bundle" if mode == "fused" else "region"
+    dist.barrier(peer_out.group)      # NCCL: stream-ordered after this rank's kernels, completes when all joined
     return peer_out.gathered() if gathered else peer_out.raw
 
 

@@ -209,6 +209,14 @@ int ctb_ipc_alloc(size_t bytes, int device, void** ptr, void* handle_out);
 int ctb_ipc_open(const void* handle, int device, void** ptr);
 int ctb_ipc_close(void* ptr, int device);
 int ctb_ipc_free(void* ptr, int device);
+/* The gather as a push: copy columns [t0, t0 + n_cols) of n_rows rows (leading dimension ld, doubles)
+ * of `src` (this GPU) to the same place in each of the n_peers mapped buffers (a pointer equal to `src`
+ * is skipped).  One kernel, every row piece read once and stored to all peers with coalesced stores
+ * over NVLink; stream-ordered.  For 4 and more ranks this beats both NCCL's all_gather + layout copy and
+ * the stores fused into the aggregation kernel's epilogue (ctb_agg_opts.peer_out), whose 256-byte
+ * pieces per region and tile are too scattered for 8 destinations. */
+int ctb_push_rows(const double* src, int64_t ld, int64_t t0, int64_t n_cols, int64_t n_rows, int n_peers,
+                  double* const* peers, void* stream);
 
 /* ---- pointwise helpers (materialising what the reference materialises) --- */
 /* out[j][i] = f_j(x0[i], x1[i]) for i < n; DEVICE pointers (transformations.py:69-89,189). */
