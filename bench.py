@@ -553,13 +553,13 @@ def run_ours(args):
         sizes = shard_sizes(T, world)
         # the gather fused into the kernel: the epilogue stores every region-day into all ranks' buffers
         # over NVLink peer memory (CUDA IPC) -- no collective, no staging copy
-        p2p_ms = push_ms = push1_ms = p2p_err = same = same_push = None
+        p2p_ms = push_ms = p2p_err = same = same_push = None
         try:
             po = PeerOutput(plan, T, n_out)
             ref, _ = aggregate_shard_overlapped(plan, x, None, ncell, T, kind, PARAMS[kind], n_out, pieces=1)
             ref = torch.nan_to_num(ref)
 
-            def p2p(mode, pieces=2):
+            def p2p(mode, pieces=1):
                 return lambda: aggregate_shard_p2p(plan, x, None, ncell, T, po, kind, PARAMS[kind], n_out, mode=mode,
                                                    pieces=pieces)
             p2p_ms, _, _ = B.timed(p2p("fused"), s_steps, 3)
@@ -570,8 +570,7 @@ def run_ours(args):
             po.raw.zero_()
             torch.cuda.synchronize()
             dist.barrier()
-            push1_ms, _, _ = B.timed(p2p("push", 1), s_steps, 3)
-            push_ms, _, _ = B.timed(p2p("push", 2), s_steps, 3)
+            push_ms, _, _ = B.timed(p2p("push", 1), s_steps, 3)
             torch.cuda.synchronize()
             same_push = bool(torch.equal(torch.nan_to_num(po.gathered()), ref))
             del ref
@@ -585,13 +584,13 @@ def run_ours(args):
                   "nccl_compute_plus_gather_ms": seq_ms, "nccl_overlapped_4_pieces_ms": ovl_ms,
                   "nccl_gather_ms": seq_ms - comp_ms,
                   "p2p_fused_kernel_ms": p2p_ms, "p2p_equal_to_nccl_result": same,
-                  "p2p_push_ms": push_ms, "p2p_push_one_piece_ms": push1_ms, "p2p_push_equal_to_nccl_result": same_push, "p2p_error": p2p_err,
+                  "p2p_push_ms": push_ms, "p2p_push_equal_to_nccl_result": same_push, "p2p_error": p2p_err,
                   "bytes_received_per_rank": int(8 * n_out * plan.R * (T - min(sizes))),
                   "value": plan.R * T / (best * 1e-3), "value_compute_only": plan.R * T / (comp_ms * 1e-3),
                   "unit": "region-days/s", "scaling": "strong",
                   "limiter": "NVLink: every rank receives (N-1)/N of the 285 MB fp64 output; the fused kernel hides "
-                             "it behind the aggregation's own stores (best at N=2), the push kernel sends it as "
-                             "coalesced row pieces after the aggregation (best from N=4), the NCCL path adds an "
+                             "it behind the aggregation's own stores (best at N=2 and 4), the push kernel sends it as "
+                             "coalesced row pieces after the aggregation (best at N=8), the NCCL path adds an "
                              "all_gather and a strided copy"}
         plan.__dict__.pop("_shard_buffers", None)
 

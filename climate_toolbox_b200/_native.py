@@ -41,6 +41,7 @@ class AggOpts(C.Structure):
                 ("day_of_year", C.c_void_p), ("peer_out", C.POINTER(C.c_void_p)), ("peer_row", C.c_void_p)]
 
 
+PUSH_SM, PUSH_COPY_ENGINE = 0, 1
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
 
@@ -117,7 +118,7 @@ def lib():
     L.ctb_ipc_free.restype = C.c_int
     L.ctb_ipc_free.argtypes = [vp, C.c_int]
     L.ctb_push_rows.restype = C.c_int
-    L.ctb_push_rows.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(vp), vp]
+    L.ctb_push_rows.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(vp), C.c_int, vp]
     L.ctb_transform.restype = C.c_int
     L.ctb_transform.argtypes = [vp, vp, C.c_int, i64, C.c_int, dp, C.c_int, C.c_int, vp, vp]
     L.ctb_gather_rows.restype = C.c_int

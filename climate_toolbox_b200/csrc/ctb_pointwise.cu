@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const double* __restrict
 }  // namespace
 
 extern "C" int ctb_push_rows(const double* src, int64_t ld, int64_t t0, int64_t n_cols, int64_t n_rows, int n_peers,
-                             double* const* peers, void* stream) {
+                             double* const* peers, int engine, void* stream) {
   if (n_peers < 0 || n_peers > CTB_MAX_PEERS || ld < 0 || t0 < 0 || n_cols < 0 || n_rows < 0 || t0 + n_cols > ld ||
       n_cols >= (1ll << 31)) {
     ctb_set_error("ctb_push_rows: bad shape (ld=%lld t0=%lld n_cols=%lld n_rows=%lld n_peers=%d)", (long long)ld,
@@ -171,6 +171,13 @@ extern "C" int ctb_push_rows(const double* src, int64_t ld, int64_t t0, int64_t 
     if (peers[p] != src) pp.p[n++] = peers[p];
   }
   if (n == 0) return CTB_OK;
+  if (engine == CTB_PUSH_COPY_ENGINE) {
+    for (int p = 0; p < n; ++p)
+      CTB_CUDA(cudaMemcpy2DAsync(pp.p[p] + t0, (size_t)ld * 8, src + t0, (size_t)ld * 8, (size_t)n_cols * 8, (size_t)n_rows,
+                                 cudaMemcpyDefault, (cudaStream_t)stream));
+    return CTB_OK;
+  }
+  if (engine != CTB_PUSH_SM) { ctb_set_error("ctb_push_rows: engine %d", engine); return CTB_ERR_INVALID; }
   const unsigned grid = (unsigned)std::min<int64_t>((n_rows + 7) / 8, 148 * 8);
   push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, t0, (int)n_cols, n_rows, n, pp);
   CTB_LAUNCH_CHECK();

@@ -241,7 +241,7 @@ class PeerOutput:
             self._side = torch.cuda.Stream(self.plan.device)
         return self._side
 
-    def push(self, t0, n):
+    def push(self, t0, n, copy_engine=False):
         """Copy columns ``[t0, t0 + n)`` of this rank's buffer into every peer's (``ctb_push_rows``)."""
         import ctypes as C
 
@@ -249,7 +249,8 @@ class PeerOutput:
         from . import _native as N
         arr = (C.c_void_p * self.world)(*self.ptrs)
         N.check(N.lib().ctb_push_rows(C.c_void_p(self._own), self.T, t0, n, self.n_out * self.plan.R, self.world,
-                                      arr, E._stream_ptr(self.plan.device)))
+                                      arr, N.PUSH_COPY_ENGINE if copy_engine else N.PUSH_SM,
+                                      E._stream_ptr(self.plan.device)))
 
     def close(self):
         from . import _native as N
@@ -274,17 +275,18 @@ def _tensor_from_ptr(ptr, shape, device, owner):
 
 
 def aggregate_shard_p2p(plan, x0, x1, stride, T, peer_out, kind="identity", params=(), n_out=1, gathered=True,
-                        mode="auto", pieces=2):
+                        mode="auto", pieces=1):
     """Time-sharded aggregation whose gather needs no collective: this rank aggregates days
     ``shard_range(T)`` of ``x0`` and every rank ends with the full ``[n_out, R, T]`` result in its own
     peer-mapped buffer (``peer_out``: a :class:`PeerOutput`).
 
     ``mode="fused"``: the kernel's epilogue stores every region-day to column ``t`` of ALL ranks'
-    buffers (rows in the plan's bundle order, ``peer_out.row_of_region``; best for 2 ranks).
+    buffers (rows in the plan's bundle order, ``peer_out.row_of_region``; best up to 4 ranks).
     ``mode="push"``: the kernel writes this rank's own buffer and one copy kernel
     (``ctb_push_rows``) sends the finished column block to every peer as coalesced row pieces (best
-    from 4 ranks: the fused form's 256-byte pieces per region and tile are too scattered for many
-    destinations; in ``pieces`` time pieces, the push of one under the kernel of the next).
+    for 8 ranks: the fused form's 256-byte pieces per region and tile are too scattered for many
+    destinations).  ``pieces`` > 1 pushes piece k by DMA under the kernel of piece k+1 -- measured
+    slower (2-D DMA of narrow row pieces; a copy kernel cannot share an SM with the aggregation's CTAs).
     ``"auto"`` picks by the group size.  A stream-ordered barrier ends the call;
     the result comes back in the reference's label order when ``gathered`` (else ``peer_out.raw``
     in the order ``peer_out.rows`` names)."""
@@ -292,7 +294,7 @@ def aggregate_shard_p2p(plan, x0, x1, stride, T, peer_out, kind="identity", para
     from . import _native as N
     world, rank = peer_out.world, peer_out.rank
     if mode == "auto":
-        mode = "fused" if world <= 2 else "push"
+        mode = "fused" if world <= 4 else "push"
     if mode not in ("fused", "push"):
         raise ValueError("mode must be 'auto', 'fused' or 'push'")
     t0, t1 = shard_range(T, world, rank)
@@ -320,8 +322,8 @@ def aggregate_shard_p2p(plan, x0, x1, stride, T, peer_out, kind="identity", para
                     ev = torch.cuda.Event()
                     ev.record(main)
                     side.wait_event(ev)
-                    with torch.cuda.stream(side):
-                        peer_out.push(t0 + p0, m)
+                    with torch.cuda.stream(side):      # DMA: the kernel's CTAs leave no room for a copy kernel
+                        peer_out.push(t0 + p0, m, copy_engine=True)
                 else:
                     peer_out.push(t0 + p0, m)
             if n > step:

@@ -214,9 +214,13 @@ int ctb_ipc_free(void* ptr, int device);
  * is skipped).  One kernel, every row piece read once and stored to all peers with coalesced stores
  * over NVLink; stream-ordered.  For 4 and more ranks this beats both NCCL's all_gather + layout copy and
  * the stores fused into the aggregation kernel's epilogue (ctb_agg_opts.peer_out), whose 256-byte
- * pieces per region and tile are too scattered for 8 destinations. */
+ * pieces per region and tile are too scattered for 8 destinations.
+ * engine: CTB_PUSH_SM = the copy kernel; CTB_PUSH_COPY_ENGINE = one 2-D DMA per peer (no SM: the only
+ * form that overlaps a running aggregation kernel, whose CTAs hold every register of their SM). */
+#define CTB_PUSH_SM 0
+#define CTB_PUSH_COPY_ENGINE 1
 int ctb_push_rows(const double* src, int64_t ld, int64_t t0, int64_t n_cols, int64_t n_rows, int n_peers,
-                  double* const* peers, void* stream);
+                  double* const* peers, int engine, void* stream);
 
 /* ---- pointwise helpers (materialising what the reference materialises) --- */
 /* out[j][i] = f_j(x0[i], x1[i]) for i < n; DEVICE pointers (transformations.py:69-89,189). */

@@ -51,9 +51,9 @@ def test_invalid_calls_fail_cleanly_without_gpu(built):
         _native.check(rc)
     assert built.ctb_aggregate_workspace_bytes(None, 10, 1) == 0
     # ctb_push_rows: a column block that does not fit the leading dimension, too many peers
-    assert built.ctb_push_rows(None, 10, 8, 4, 1, 1, None, None) == _native.ERR_INVALID
-    assert built.ctb_push_rows(None, 10, 0, 4, 1, _native.MAX_PEERS + 1, None, None) == _native.ERR_INVALID
-    assert built.ctb_push_rows(None, 10, 0, 0, 1, 1, None, None) == 0          # nothing to copy
+    assert built.ctb_push_rows(None, 10, 8, 4, 1, 1, None, 0, None) == _native.ERR_INVALID
+    assert built.ctb_push_rows(None, 10, 0, 4, 1, _native.MAX_PEERS + 1, None, 0, None) == _native.ERR_INVALID
+    assert built.ctb_push_rows(None, 10, 0, 0, 1, 1, None, 0, None) == 0          # nothing to copy
 
 
 def test_missing_library_fails_loudly(monkeypatch):
