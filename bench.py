@@ -49,9 +49,10 @@ METRIC = "region-days/sec"
 PARAMS = {"identity": (), "poly": (273.15, 1, 2, 3, 4), "edd": (283.15, 303.15)}
 KERNEL = {"identity": "agg_stream_kernel", "poly": "agg_stream_kernel", "edd": "agg_stream_kernel"}
 # fp64-pipe lane slots per CSR entry and day of the Snyder kernel (2 thresholds): executed DFMA + DMUL + DADD +
-# DSETP warp instructions x 32 / entry-days (profiles/r2_ncu_full_agg_stream_kernel_config4.json: 833 M warp
-# instructions for 3.07e8 entry-days); 64 fp64 lanes per SM and clock
-SNYDER_FP64_OPS_PER_ENTRY_DAY = 87
+# DSETP warp instructions x 32 / entry-days (profiles/r2_ncu_full_agg_stream_kernel_config4.json: 690 M warp
+# instructions for 3.07e8 entry-days; the zero-weight padding of the quads is overhead, not work); 64 fp64
+# lanes per SM and clock
+SNYDER_FP64_OPS_PER_ENTRY_DAY = 72
 FP64_LANES_PER_SM_CLK = 64
 
 

@@ -8,6 +8,7 @@
 //                      out[r][t] = (sum of the region's partial rows, fixed order) / den[r].
 //   agg_group_finish_kernel  fused time reduction: per-tile partial sums -> output columns.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -327,13 +328,18 @@ int ctb_pack_transform(int transform, const double* params, int n_params, int n_
       }
       return CTB_OK;
     case CTB_TR_EDD:
-      if (!need(n_out)) return CTB_ERR_INVALID;
-      for (int j = 0; j < n_out; ++j) out->a[j] = params[j];
+    case CTB_TR_GDD: {
+      const int n = transform == CTB_TR_EDD ? n_out : 2 * n_out;
+      if (!need(n)) return CTB_ERR_INVALID;
+      for (int j = 0; j < n; ++j) {
+        const double e = params[j];
+        out->a[j] = e;
+        const float f = (float)e;          // nearest; then the neighbours that bracket e
+        out->up[j] = (double)f < e ? std::nextafterf(f, INFINITY) : f;
+        out->dn[j] = (double)f > e ? std::nextafterf(f, -INFINITY) : f;
+      }
       return CTB_OK;
-    case CTB_TR_GDD:
-      if (!need(2 * n_out)) return CTB_ERR_INVALID;
-      for (int j = 0; j < 2 * n_out; ++j) out->a[j] = params[j];
-      return CTB_OK;
+    }
   }
   ctb_set_error("transform=%d unsupported", transform);
   return CTB_ERR_INVALID;

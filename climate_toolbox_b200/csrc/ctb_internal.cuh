@@ -159,6 +159,9 @@ struct ctb_time_groups {
 struct CtbTr {
   double a[8];  // thresholds / offset
   int ip[4];    // integer powers (POLY)
+  // Snyder thresholds rounded to single precision, up and down: for a float x, x < e <=> x < up(e)
+  // and x > e <=> x > dn(e), so the case tests of float inputs run on the fp32 pipe
+  float up[8], dn[8];
 };
 
 // internal transform kind: CTB_TR_POLY whose orders are 1..n_out (checked on the host by the
@@ -207,21 +210,20 @@ __device__ __forceinline__ double ctb_rcp_pos(double w) {
   r = fma(r, fma(-w, r, 1.0), r);
   return fma(r, fma(-w, r, 1.0), r);     // w = 0 / inf / NaN: NaN or inf, only used by unselected forms
 }
-__device__ __forceinline__ double ctb_sqrt01(double v) {   // v in [0, 1] (or NaN)
+__device__ __forceinline__ double ctb_sqrt_pos(double v) {   // v in (0, 1]
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
   const double h = 0.5 * y;
   double s = v * y;
   s = fma(fma(-s, s, v), h, s);
-  s = fma(fma(-s, s, v), h, s);
-  return v > 0.0 ? s : v;                                  // v = 0: 0 (not 0 * inf); NaN stays NaN
+  return fma(fma(-s, s, v), h, s);
 }
 
-__device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
+__device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1)
   const double v = 1.0 - a;
-  const double t = fma(2.0, v, -1.0);
-  // even/odd split H(t) = E(t^2) + t*O(t^2): two independent Horner chains of 8 instead of one of
-  // 16 (the Snyder kernels stall on this dependency chain: 4 warps per scheduler); same 3.5e-16.
+  const double t = fma(-2.0, a, 1.0);   // = 2 v - 1
+  // even/odd split H(t) = E(t^2) + t*O(t^2): two independent Horner chains instead of one (the
+  // Snyder kernels stall on this dependency chain: 4-5 warps per scheduler)
   static_assert(CTB_EDD_H_N % 2 == 1 && CTB_EDD_H_N >= 5, "even/odd split below assumes an even degree");
   constexpr int D = CTB_EDD_H_N - 1;
   const double t2 = t * t;
@@ -230,7 +232,7 @@ __device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
   for (int k = D - 2; k >= 0; k -= 2) pe = fma(pe, t2, ctb_edd_H[k]);
 #pragma unroll
   for (int k = D - 3; k >= 1; k -= 2) po = fma(po, t2, ctb_edd_H[k]);
-  return v * ctb_sqrt01(v) * fma(po, t, pe);
+  return v * ctb_sqrt_pos(v) * fma(po, t, pe);
 }
 
 // Branch-free: a warp's lanes hold different gridcell-days, so the three cases of the closed form
@@ -238,13 +240,37 @@ __device__ __forceinline__ double ctb_edd_g(double a) {   // a in [0, 1]
 // branches, a quarter of the instructions control flow).  The straddling form is evaluated for all
 // lanes -- its argument clamped into the polynomial's range -- and the case is picked by selects;
 // what an unselected form computes from NaN / W = 0 never reaches the result.
-__device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double rW,
-                                          double e) {
-  const double s = (e - M) * rW, a = fmin(fabs(s), 1.0);   // fmin(NaN, 1) = 1
+// The fp64 pipe is the unit this kernel keeps busiest (ncu: 61 %), and double comparisons run on it:
+// the clamp and the sign test below read the high word instead (positive doubles order like their bit
+// patterns), and |s| is clamped just below 1 so that v = 1 - a is never 0 and the square root needs no
+// special case (g(1 - 2^-53) = 1e-24: the straddling form is only selected for tmin < e < tmax, |s| < 1).
+// |x| and -x through the high word (integer pipe): as fp64 instructions they are DADDs on the pipe
+// the Snyder kernels saturate first
+__device__ __forceinline__ double ctb_abs_bits(double x) {
+  return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+}
+__device__ __forceinline__ double ctb_neg_bits(double x) {
+  return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+// the straddling form when tmin < e, else M - e; the caller zeroes (or skips) tmin < e && !(tmax > e)
+__device__ __forceinline__ double ctb_edd_pick(bool tmin_below, double M, double W, double rW, double e) {
+  const double d = e - M, s = d * rW;
+  const int hi = __double2hiint(s);
+  // 1 <= |s| < inf: clamp; inf / NaN (non-finite temperatures) pass through and give NaN like the
+  // reference's arcsin
+  const bool big = (unsigned)((hi & 0x7fffffff) - 0x3ff00000) < 0x40000000u;
+  const double a = big ? 0.99999999999999989 : ctb_abs_bits(s);
   const double g = ctb_edd_g(a);
-  const double straddle = W * (s < 0.0 ? g + a : g);
-  const double below = tmax > e ? straddle : 0.0;            // tmax <= e or NaN: no degree days
-  return tmin < e ? below : M - e;                           // tmin >= e or NaN: M - e
+  const double straddle = W * (hi < 0 ? g + a : g);                        // g(-a) = g(a) + a
+  return tmin_below ? straddle : ctb_neg_bits(d);                          // tmin >= e or NaN: M - e
+}
+__device__ __forceinline__ double ctb_edd_cases(bool tmin_below, bool tmax_above, double M, double W, double rW,
+                                                double e) {
+  const double r = ctb_edd_pick(tmin_below, M, W, rW, e);
+  return (tmin_below && !tmax_above) ? 0.0 : r;                            // tmax <= e or NaN: no degree days
+}
+__device__ __forceinline__ double ctb_edd(double tmin, double tmax, double M, double W, double rW, double e) {
+  return ctb_edd_cases(tmin < e, tmax > e, M, W, rW, e);
 }
 
 template <int KIND, int NOUT>
@@ -284,6 +310,28 @@ __device__ __forceinline__ void ctb_apply(const CtbTr& P, double x0, double x1, 
 #pragma unroll
     for (int j = 0; j < NOUT; ++j)
       f[j] = ctb_edd(x0, x1, M, W, rW, P.a[2 * j]) - ctb_edd(x0, x1, M, W, rW, P.a[2 * j + 1]);
+  }
+}
+
+// Two-input transforms on the stored type: float inputs take the case tests in single precision
+// against the rounded thresholds of CtbTr (exactly the same decisions; two DSETP fewer per evaluation).
+template <int KIND, int NOUT, typename TIN>
+__device__ __forceinline__ void ctb_apply2(const CtbTr& P, TIN lo, TIN hi, double (&f)[NOUT]) {
+  static_assert(KIND == CTB_TR_EDD || KIND == CTB_TR_GDD, "two-input transforms");
+  if constexpr (sizeof(TIN) == 8) {
+    ctb_apply<KIND, NOUT>(P, lo, hi, f);
+  } else {
+    const double x0 = (double)lo, x1 = (double)hi;
+    const double M = (x1 + x0) * 0.5, W = (x1 - x0) * 0.5, rW = ctb_rcp_pos(W);
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) {
+      if constexpr (KIND == CTB_TR_EDD) {
+        f[j] = ctb_edd_cases(lo < P.up[j], hi > P.dn[j], M, W, rW, P.a[j]);
+      } else {
+        f[j] = ctb_edd_cases(lo < P.up[2 * j], hi > P.dn[2 * j], M, W, rW, P.a[2 * j]) -
+               ctb_edd_cases(lo < P.up[2 * j + 1], hi > P.dn[2 * j + 1], M, W, rW, P.a[2 * j + 1]);
+      }
+    }
   }
 }
 

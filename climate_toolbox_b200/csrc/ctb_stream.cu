@@ -321,6 +321,9 @@ __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t ti
 // Two-input transforms (Snyder EDD / GDD from tasmin, tasmax): the same quad loop, the lane's entry
 // evaluated on its four days.  fp64 ALU bound; NaN results are skipped by a select (the reference's
 // skipna sum), and the zero-weight padding of the last quad never meets a value (0 * inf).
+#ifndef CTB_EDD_UNROLL
+#define CTB_EDD_UNROLL 1
+#endif
 template <typename TIN, int KIND, int NOUT, bool GATE>
 __device__ __forceinline__ void reduce_region2(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
                                                int lane, const int (&doy)[4], double (&v)[NOUT]) {
@@ -330,6 +333,8 @@ __device__ __forceinline__ void reduce_region2(const CtbTr& tr, uint32_t tile_a,
   for (int g = 0; g < 4; ++g)
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) acc[g][j] = 0.0;
+  constexpr int UNR = CTB_EDD_UNROLL;
+#pragma unroll(UNR)
   for (int q = 0; q < nq; ++q, ent_a += 4 * (uint32_t)sizeof(CtbEnt)) {
     const uint4 m = lds_u4(ent_a);
     const double w = __hiloint2double((int)m.y, (int)m.x);
@@ -345,11 +350,24 @@ __device__ __forceinline__ void reduce_region2(const CtbTr& tr, uint32_t tile_a,
     gate4<GATE>(m.w, doy, on);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      double f[NOUT];
-      ctb_apply<KIND, NOUT>(tr, (double)lo[g], (double)hi[g], f);
+      if constexpr (KIND == CTB_TR_EDD && sizeof(TIN) == 4) {
+        // the "no degree days" case (tmin < e, tmax <= e) adds nothing: it joins the predicate of the
+        // FMA instead of costing a select of its own
+        const double x0 = (double)lo[g], x1 = (double)hi[g];
+        const double M = (x1 + x0) * 0.5, W = (x1 - x0) * 0.5, rW = ctb_rcp_pos(W);
 #pragma unroll
-      for (int j = 0; j < NOUT; ++j)
-        acc[g][j] = fma(w, (wnz && on[g] && f[j] == f[j]) ? f[j] : 0.0, acc[g][j]);
+        for (int j = 0; j < NOUT; ++j) {
+          const bool tb = lo[g] < tr.up[j], ta = hi[g] > tr.dn[j];
+          const double r = ctb_edd_pick(tb, M, W, rW, tr.a[j]);
+          if (wnz && on[g] && (ta || !tb) && r == r) acc[g][j] = fma(w, r, acc[g][j]);
+        }
+      } else {
+        double f[NOUT];
+        ctb_apply2<KIND, NOUT, TIN>(tr, lo[g], hi[g], f);
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j)
+          if (wnz && on[g] && f[j] == f[j]) acc[g][j] = fma(w, f[j], acc[g][j]);
+      }
     }
   }
 #pragma unroll
@@ -621,6 +639,15 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
 #ifndef CTB_POLY34_THREADS
 #define CTB_POLY34_THREADS 640
 #endif
+#ifndef CTB_EDD1_THREADS
+#define CTB_EDD1_THREADS 640
+#endif
+#ifndef CTB_EDD2_THREADS
+#define CTB_EDD2_THREADS 384
+#endif
+#ifndef CTB_EDD34_THREADS
+#define CTB_EDD34_THREADS 512
+#endif
 template <typename TIN, int KIND, int NOUT>
 int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   // 32 warps of 64 registers; the multi-output polynomials keep 4 fp64 accumulators per output and
@@ -628,7 +655,13 @@ int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   // ... and the Snyder forms 16 warps of 128 registers (fp64 ALU bound: registers buy more than warps)
   constexpr int NIN = NIn<KIND>::v;
   constexpr bool POLY = KIND == CTB_TR_POLY || KIND == CTB_TR_POLY_SEQ;
-  constexpr int THREADS = NIN == 2 ? (NOUT <= 2 ? 640 : 512) : (POLY && NOUT > 2) ? CTB_POLY34_THREADS : (POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
+  // Snyder forms: threshold evaluations per gridcell-day -- few warps with many registers: the compiler
+  // interleaves the 4 days x EVALS dependency chains of a quad inside one warp (measured, config 4:
+  // 768/640/512/448/384/256 threads = 4.53/4.33/4.12/4.49/3.91/5.31 ms; consumer warps a multiple of 4;
+  // EDD with 3 or 4 thresholds: 512 threads 3.00/3.92 ms per 730 days, 384 threads 3.03/4.24;
+  // GDD with 2 outputs: 3.57 / 3.28)
+  constexpr int EVALS = KIND == CTB_TR_GDD ? 2 * NOUT : NOUT;
+  constexpr int THREADS = NIN == 2 ? (EVALS == 1 ? CTB_EDD1_THREADS : (EVALS == 2 || KIND == CTB_TR_GDD) ? CTB_EDD2_THREADS : CTB_EDD34_THREADS) : (POLY && NOUT > 2) ? CTB_POLY34_THREADS : (POLY && NOUT > 1) ? 768 : CTB_STREAM_THREADS;
   constexpr int S = CTB_STAGES;   // tile stages: one being reduced, up to two landing
   constexpr size_t SMEM = (size_t)S * Geo<NIN>::TILE_BYTES + 2 * CTB_META_CAP;
   static_assert(SMEM <= 227 * 1024 - 512, "shared memory budget");
