@@ -87,7 +87,10 @@ constexpr int CTB_META_CAP = CTB_META_A_CAP + CTB_META_B_CAP;     // 14,848 B: o
 // shared-memory load fall into 32 different banks.
 constexpr int CTB_ROWB = CTB_TILE_UNITS * 16 + 16;                 // 2,064 B
 constexpr int CTB_STREAM_TILE_BYTES = CTB_TB * CTB_ROWB;           // 66,048 B per input
-constexpr int CTB_STREAM_THREADS = 1024;
+#ifndef CTB_STREAM_THREADS_OVERRIDE
+#define CTB_STREAM_THREADS_OVERRIDE 768
+#endif
+constexpr int CTB_STREAM_THREADS = CTB_STREAM_THREADS_OVERRIDE;
 constexpr int CTB_STREAM_PRODUCER_WARPS = 4;
 
 // the planner sizes bundles against this budget: 128 pieces x 4 cells x 33 x 4 bytes (the round-1

@@ -1,10 +1,10 @@
 // The streaming kernel: stage + gather + segmented weighted sum for TIME_MAJOR inputs
-// [T][lat][lon] (the BCSD layout), IDENTITY and POLY transforms.
+// [T][lat][lon] (the BCSD layout), all transforms.
 //
 // Replaces climate_toolbox/aggregations/aggregations.py:27 (gather) and :75-82
 // (sum(w*x)/sum(w) per region), with transformations.py:189 fused in.
 //
-// One persistent CTA of 32 warps per SM.  A work unit = one bundle (spatially adjacent regions
+// One persistent CTA of 24 warps per SM (fewer, with more registers, for the multi-output and Snyder forms).  A work unit = one bundle (spatially adjacent regions
 // whose gridcell footprint fits a shared-memory tile) x a chunk of consecutive 32-day blocks;
 // CTA b takes units b, b + grid, ... in chunk-major order, so that CTAs running together read
 // neighbouring bundles of the same days (the lines they share meet in L2).
@@ -16,7 +16,7 @@
 //                      armed by cp.async.mbarrier.arrive, so the copies of up to two tiles are
 //                      in flight while a third is being reduced.  The bundle's metadata blob
 //                      arrives as one cp.async.bulk (TMA 1-D) per unit, double-buffered.
-//   28 consumer warps  take the regions of a landed tile from a shared counter (longest
+//   20 consumer warps  take the regions of a landed tile from a shared counter (longest
 //                      first).  A warp reduces a region four entries at a time: lane = (entry
 //                      in quad) x 8 + (day mod 8); one 16-byte shared load brings the lane its
 //                      entry's {weight, column offset}, four conflict-free 4-byte loads bring
@@ -268,6 +268,9 @@ __device__ __forceinline__ void reduce_region(const CtbTr& tr, uint32_t tile_a, 
 #ifndef CTB_POLY34_UNROLL
 #define CTB_POLY34_UNROLL 2
 #endif
+#ifndef CTB_QUAD_UNROLL
+#define CTB_QUAD_UNROLL 2
+#endif
 template <int KIND, int NOUT, bool GATE>
 __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t tile_a, uint32_t ent_a, int nq,
                                                     int lane, const int (&doy)[4], double (&v)[NOUT]) {
@@ -281,7 +284,7 @@ __device__ __forceinline__ bool reduce_region_widen(const CtbTr& tr, uint32_t ti
   auto widen = [](uint32_t b) {
     return __longlong_as_double((long long)((unsigned long long)b * 0x20000000ull + 0x3800000000000000ull));
   };
-  constexpr int UNR = NOUT > 2 ? CTB_POLY34_UNROLL : 2;
+  constexpr int UNR = NOUT > 2 ? CTB_POLY34_UNROLL : CTB_QUAD_UNROLL;
 #pragma unroll(UNR)
   for (int q = 0; q < nq; ++q, ent_a += 4 * (uint32_t)sizeof(CtbEnt)) {
     const uint4 m = lds_u4(ent_a);
@@ -650,9 +653,9 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
 #endif
 template <typename TIN, int KIND, int NOUT>
 int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
-  // 32 warps of 64 registers; the multi-output polynomials keep 4 fp64 accumulators per output and
-  // lane and take 24 warps of 80 registers (3 and 4 outputs: 20 warps of 96) instead of spilling
-  // ... and the Snyder forms 16 warps of 128 registers (fp64 ALU bound: registers buy more than warps)
+  // 24 warps of 80 registers (measured, config 2: 1024 / 896 / 768 / 640 / 512 threads = 0.619 / 0.609 /
+  // 0.599 / 0.611 / 0.672 ms; the reduction alone is fastest with 32 warps, the whole kernel with 24);
+  // three and four polynomial outputs keep 4 fp64 accumulators per output and lane: 20 warps of 96
   constexpr int NIN = NIn<KIND>::v;
   constexpr bool POLY = KIND == CTB_TR_POLY || KIND == CTB_TR_POLY_SEQ;
   // Snyder forms: threshold evaluations per gridcell-day -- few warps with many registers: the compiler
