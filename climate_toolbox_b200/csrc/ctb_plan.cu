@@ -831,6 +831,9 @@ extern "C" int ctb_host_pack(const ctb_plan* P, const void* x, int dtype, int64_
 // touches the data -- what the ranks of a multi-GPU job need when they share the host's cores.
 // Thread = one packed piece x 4 consecutive days (4 independent 16-byte loads in flight per
 // thread); reads are contiguous along a run of referenced pieces, writes are fully coalesced.
+#ifndef CTB_PULL_L2_HINT
+#define CTB_PULL_L2_HINT ""      // experiments: ".L2::64B" / ".L2::256B" fetch-size hints (profiles/micro/r2_e2e_ingest.log)
+#endif
 namespace {
 __global__ void __launch_bounds__(256) pull_pack_kernel(const uint4* __restrict__ src, int64_t stride16,
                                                         const int32_t* __restrict__ tix, int64_t t_begin, int T,
@@ -848,7 +851,7 @@ __global__ void __launch_bounds__(256) pull_pack_kernel(const uint4* __restrict_
     for (int k = 0; k < 4; ++k)
       if (d0 + k < T) {
         const int64_t tp = tix ? tix[t_begin + d0 + k] : t_begin + d0 + k;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+        asm volatile("ld.global.nc.L1::no_allocate" CTB_PULL_L2_HINT ".v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(src + tp * stride16 + so));
       }
 #pragma unroll
