@@ -377,7 +377,9 @@ __device__ __forceinline__ void reduce_region2(const CtbTr& tr, uint32_t tile_a,
   for (int j = 0; j < NOUT; ++j) v[j] = fold_quads(acc[0][j], acc[1][j], acc[2][j], acc[3][j], lane);
 }
 
-template <typename TIN, int KIND, int NOUT, int THREADS, int S, bool GATE>
+// TIX: the launch has a time index (its own instantiation: the two producer loops compile differently,
+// and carrying both costs the plain one 2 %)
+template <typename TIN, int KIND, int NOUT, int THREADS, int S, bool GATE, bool TIX>
 __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a) {
   constexpr int NIN = NIn<KIND>::v;
   using G = Geo<NIN>;
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
     const TIN* const X0 = reinterpret_cast<const TIN*>(a.x0);
     const TIN* const X1 = NIN == 2 ? reinterpret_cast<const TIN*>(a.x1) : X0;
     const int64_t row_step = 4 * a.stride;
+    const int64_t stride_b = a.stride * (int64_t)sizeof(TIN);
     // this lane's unit groups: group G = pw + NP * gi of the stage's 16 (input G / GROUPS_IN, units
     // (G % GROUPS_IN) * 8 + l8 of that input); dst_of[gi]: byte offset inside the stage's row 0
     int unit_of[UPW];
@@ -479,7 +482,24 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
       for (int gi = 0; gi < UPW; ++gi) ok[gi] = pw + NP * gi < NG && unit_of[gi] < d.w;
       const int tb_begin = (unit / a.n_bundles) * a.chunk_tb;
       const int tb_end = min(tb_begin + a.chunk_tb, a.n_tb);
+      int planeN[CTB_TB / 4] = {};
+      auto load_plane = [&](int tb, int dd) {
+        const int t = tb * CTB_TB + dd * 4 + l4;
+        return t < a.T ? __ldg(a.tix + t) : 0;
+      };
       for (int tb = tb_begin; tb < tb_end; ++tb) {
+        // physical planes of this lane's 8 day rows (time_index: leap days removed, a ring of year
+        // buffers ...): 8 independent loads issued before the wait for the stage, not one dependent
+        // load in front of every row's copies
+        int plane[CTB_TB / 4];
+        if constexpr (TIX) {
+#pragma unroll
+          for (int dd = 0; dd < CTB_TB / 4; ++dd) plane[dd] = tb == tb_begin ? load_plane(tb, dd) : planeN[dd];
+          if (tb + 1 < tb_end) {   // ... and the next tile's a whole tile ahead
+#pragma unroll
+            for (int dd = 0; dd < CTB_TB / 4; ++dd) planeN[dd] = load_plane(tb + 1, dd);
+          }
+        }
         mbar_wait_a(empty_a + stage * 8, phase ^ 1);   // the stage's previous tile is reduced
         if (leader) {
           s_desc[stage] = make_int4(tb * CTB_TB, m | (tb == tb_begin ? F_FIRST : 0) | (tb == tb_end - 1 ? F_LAST : 0), tb, 0);
@@ -492,7 +512,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
           // one 64-bit multiply-add per copy: the row pointer advances by 4 day planes per step
           uint32_t dst = tiles_a + (uint32_t)stage * CTB_STREAM_TILE_BYTES + (uint32_t)(l4 * CTB_ROWB);
           const int n_days = min(CTB_TB, a.T - tb * CTB_TB);
-          if (a.tix == nullptr) {
+          if constexpr (!TIX) {
             int64_t ro = (int64_t)(tb * CTB_TB + l4) * a.stride;
 #pragma unroll
             for (int dd = 0; dd < CTB_TB / 4; ++dd, dst += 4 * CTB_ROWB, ro += row_step) {
@@ -506,14 +526,23 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
 #endif
             }
           } else {
-#pragma unroll 2
+#pragma unroll
             for (int dd = 0; dd < CTB_TB / 4; ++dd, dst += 4 * CTB_ROWB) {
               if (dd * 4 + l4 < n_days) {
-                const int64_t ro = (int64_t)__ldg(a.tix + tb * CTB_TB + dd * 4 + l4) * a.stride;
+                // byte addressing here: row pointer (64-bit, one multiply per row) + the unit's 32-bit byte
+                // offset.  (Measured: 0.69 -> 0.63 ms in this branch; the SAME form in the branch above
+                // costs it 2 %, 0.60 -> 0.61 ms, so that one keeps the element arithmetic.)
+                const int64_t ro = (int64_t)plane[dd] * stride_b;
+                const unsigned char* const r0 = reinterpret_cast<const unsigned char*>(X0) + ro;
+                const unsigned char* const r1 = reinterpret_cast<const unsigned char*>(X1) + ro;
 #pragma unroll
                 for (int gi = 0; gi < UPW; ++gi)
-                  if (ok[gi]) cp_async16(dst + dst_of[gi], (second[gi] ? X1 : X0) + ro + off[gi]);
+                  if (ok[gi])
+                    cp_async16(dst + dst_of[gi], (NIN == 2 && second[gi] ? r1 : r0) + (uint32_t)off[gi] * (uint32_t)sizeof(TIN));
               }
+#if CTB_PACE_NS > 0
+              __nanosleep(CTB_PACE_NS);
+#endif
             }
           }
         }
@@ -669,15 +698,18 @@ int launch(const ctb_plan* P, AggArgs a, cudaStream_t st) {
   constexpr size_t SMEM = (size_t)S * Geo<NIN>::TILE_BYTES + 2 * CTB_META_CAP;
   static_assert(SMEM <= 227 * 1024 - 512, "shared memory budget");
   static int n_sm[64] = {0};
-  static bool attr_set[64][2] = {{false}};
+  static bool attr_set[64][2][2] = {{{false}}};
   const int dev = P->device & 63;
   const bool gate = a.doy != nullptr;   // growing-season gate: its own instantiation (the inner loop tests it)
-  auto k = gate ? agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, true>
-                : agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, false>;
-  if (!attr_set[dev][gate]) {
+  const bool tix = a.tix != nullptr;
+  auto k = gate ? (tix ? agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, true, true>
+                       : agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, true, false>)
+                : (tix ? agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, false, true>
+                       : agg_stream_kernel<TIN, KIND, NOUT, THREADS, S, false, false>);
+  if (!attr_set[dev][gate][tix]) {
     CTB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, P->device));
     CTB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set[dev][gate] = true;
+    attr_set[dev][gate][tix] = true;
   }
   a.n_stages = S;
   a.tile_stride = Geo<NIN>::TILE_BYTES;
