@@ -1,5 +1,5 @@
 // Dispatch of ctb_aggregate / ctb_aggregate_grouped, and the kernels beside the streaming kernel
-// (ctb_stream.cu, every TIME_MAJOR input whose planes are 16-byte aligned):
+// (ctb_stream_impl.cuh, every TIME_MAJOR input whose planes are 16-byte aligned):
 //
 //   agg_direct_kernel  CELL_MAJOR input [lat][lon][T] (the reference test fixture), and the
 //                      fallback for planes that are not 16-byte aligned: one warp per
@@ -150,7 +150,7 @@ int launch_direct(const AggArgs& a, int layout, cudaStream_t st) {
   return CTB_OK;
 }
 
-// variant 1 = the streaming kernel (ctb_stream.cu), 2 = direct
+// variant 1 = the streaming kernel (ctb_stream_impl.cuh), 2 = direct
 template <typename TIN, int KIND, int NOUT>
 int run(const ctb_plan* P, const AggArgs& a, int layout, int variant, bool vec, cudaStream_t st) {
   (void)vec;

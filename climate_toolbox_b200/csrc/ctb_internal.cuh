@@ -82,7 +82,7 @@ constexpr int CTB_META_A_CAP = 32 + CTB_TILE_UNITS * 4;           // header + pi
 constexpr int CTB_META_B_CAP = 14304;                             // segment table + entries
 constexpr int CTB_META_CAP = CTB_META_A_CAP + CTB_META_B_CAP;     // 14,848 B: one whole blob
 
-// ---- streaming kernel (ctb_stream.cu): row-major tiles [day][column], filled by cp.async ----
+// ---- streaming kernel (ctb_stream_impl.cuh): row-major tiles [day][column], filled by cp.async ----
 // Row pitch: 128 units + 16 bytes, == 16 (mod 128): the 8 days x 4 columns one warp reads per
 // shared-memory load fall into 32 different banks.
 constexpr int CTB_ROWB = CTB_TILE_UNITS * 16 + 16;                 // 2,064 B
@@ -428,7 +428,7 @@ __device__ __forceinline__ void ctb_emit(const AggArgs& a, int target, double rd
   }
 }
 
-// ctb_stream.cu: the streaming kernel (IDENTITY / POLY, 16-byte aligned TIME_MAJOR planes)
+// ctb_stream_impl.cuh: the streaming kernel (IDENTITY / POLY, 16-byte aligned TIME_MAJOR planes)
 int ctb_launch_stream(const ctb_plan* P, const AggArgs& a, int dtype, int kind, int n_out, cudaStream_t st);   // a.doy != NULL: gated
 
 // RAII: make the plan's device current for the duration of an entry point
