@@ -83,6 +83,8 @@ class _GridView:
             full = [p if p is not None else np.arange(s) for p, s in zip(pos, oshape)]
             mesh = np.meshgrid(*full, indexing="ij")
             self.tix = np.ravel_multi_index([m.ravel() for m in mesh], oshape).astype(np.int64)
+            if len(self.tix) == t_phys and np.array_equal(self.tix, np.arange(t_phys)):
+                self.tix = None      # a take that keeps every step in place: the kernel without a time index
         else:
             self.tix = None
         self.on_device = isinstance(data, torch.Tensor)
