@@ -8,10 +8,12 @@ from collections import Counter
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "climate_toolbox_b200", "libctb.so")
-WANT = [("agg_stream_kernel<float, IDENTITY, 1 output, 1024 threads, 3 stages, no gate>", "agg_stream_kernelIfLi0ELi1ELi1024ELi3ELb0E"),
-        ("agg_stream_kernel<float, POLY, 4 outputs, 768 threads>", "agg_stream_kernelIfLi1ELi4ELi768ELi3ELb0E"),
-        ("agg_stream_kernel<float, EDD, 2 thresholds, 640 threads>", "agg_stream_kernelIfLi2ELi2ELi640ELi3ELb0E"),
-        ("agg_stream_kernel<float, EDD, 2 thresholds, growing-season gate>", "agg_stream_kernelIfLi2ELi2ELi640ELi3ELb1E"),
+WANT = [("agg_stream_kernel<float, IDENTITY, 1 output, 768 threads, 3 stages, no gate, no time index>", "agg_stream_kernelIfLi0ELi1ELi768ELi3ELb0ELb0E"),
+        ("agg_stream_kernel<float, IDENTITY, ..., with a time index>", "agg_stream_kernelIfLi0ELi1ELi768ELi3ELb0ELb1E"),
+        ("agg_stream_kernel<float, POLY_SEQ (orders 1..4), 4 outputs, 640 threads>", "agg_stream_kernelIfLi16ELi4ELi640ELi3ELb0ELb0E"),
+        ("agg_stream_kernel<float, EDD, 2 thresholds, 384 threads>", "agg_stream_kernelIfLi2ELi2ELi384ELi3ELb0ELb0E"),
+        ("agg_stream_kernel<float, EDD, 2 thresholds, growing-season gate>", "agg_stream_kernelIfLi2ELi2ELi384ELi3ELb1ELb0E"),
+        ("push_rows_kernel", "push_rows_kernel"),
         ("pull_pack_kernel", "pull_pack_kernel"), ("k0_match_kernel", "k0_match_kernel")]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 funcs = {}

@@ -532,6 +532,33 @@ def test_prepare_spatial_weights_data_csv(tmp_path):
     check(out.tas.values, ref, scale)
 
 
+def test_prepare_spatial_weights_data_csv_relabels_180_125(tmp_path):
+    """aggregations.py:144: pix_cent_x 180.125 is the gridcell at -179.875 -- through the CSV path of the
+    drop-in (the grid must hold -179.875, so a small 0.25-degree strip)."""
+    rng = np.random.default_rng(11)
+    lat = np.array([10.125, 10.375, 10.625, 10.875])
+    lon = -179.875 + 0.25 * np.arange(16)
+    tas = (280 + 10 * rng.standard_normal((5, len(lat), len(lon)))).astype(np.float32)
+    la, lo = np.meshgrid(lat, lon, indexing="ij")
+    csv = pd.DataFrame({"pix_cent_x": lo.ravel(), "pix_cent_y": la.ravel(),
+                        "hierid": ["R%d" % (i % 5) for i in range(la.size)],
+                        "popwt": rng.lognormal(0, 1, la.size), "areawt": rng.random(la.size) + 0.1})
+    west = csv["pix_cent_x"] == -179.875
+    csv.loc[west, "pix_cent_x"] = 180.125          # as the segment-weights files write the wrapped column
+    assert west.sum() == len(lat)
+    p = tmp_path / "weights.csv"
+    csv.to_csv(p, index=False)
+    ds = Dataset({"tas": (("time", "lat", "lon"), tas)}, coords={"time": np.arange(5), "lat": lat, "lon": lon})
+    out = weighted_aggregate_grid_to_regions(ds, "tas", "popwt", "hierid", weights=str(p))
+    w = oracle.prepare_spatial_weights_data(str(p))
+    assert (w["lon"] == -179.875).sum() == len(lat) and not (w["lon"] == 180.125).any()
+    ref, rd, labels, scale = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, w, "popwt", "hierid")
+    check(out.tas.values, ref, scale)
+    # ... and the relabelled column takes part: dropping it changes the answer
+    ref2, _, _, _ = oracle_agg(tas, ("time", "lat", "lon"), lat, lon, w[w["lon"] != -179.875], "popwt", "hierid")
+    assert np.nanmax(np.abs(ref - ref2)) > 1e-3
+
+
 # ----------------------------------------------------------------------------
 # BASELINE.json configs 3, 4, 5 and the multi-weight pass AT THEIR OWN SHAPE
 # (0.25 degree, 24,378 regions, 866+ bundles), a few days against the oracle
@@ -932,5 +959,7 @@ def test_randomized_parity(seed):
     got = out[name]
     assert list(out.hierid.values) == list(labels_o)
     got_v = got.values if got.dims == rd else got.transpose(*rd).values
+    # EDD/GDD: the kernel's polynomial form of the straddling branch is exact to 3e-14 * max(|EDD|, W)
+    # (W = half the daily range, here <= max|spread|), so W joins the scale of the 1e-9 test
     scale = scale + (np.abs(spread).max() if kind in ("edd", "gdd") else 0.0)
     check(got_v, ref, scale)
