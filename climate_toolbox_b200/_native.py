@@ -26,7 +26,7 @@ SYMBOLS = (
     "ctb_aggregate_workspace_bytes", "ctb_aggregate", "ctb_transform", "ctb_gather_rows",
     "ctb_host_pack", "ctb_pull_pack", "ctb_copy_rows_to_host", "ctb_time_groups_create", "ctb_time_groups_free", "ctb_time_groups_count",
     "ctb_aggregate_grouped_workspace_bytes", "ctb_aggregate_grouped", "ctb_aggregate_ex",
-    "ctb_ipc_alloc", "ctb_ipc_open", "ctb_ipc_close", "ctb_ipc_free", "ctb_push_rows",
+    "ctb_ipc_alloc", "ctb_ipc_open", "ctb_ipc_close", "ctb_ipc_free", "ctb_push_rows", "ctb_fingerprint",
 )
 
 
@@ -117,6 +117,8 @@ def lib():
     L.ctb_ipc_close.argtypes = [vp, C.c_int]
     L.ctb_ipc_free.restype = C.c_int
     L.ctb_ipc_free.argtypes = [vp, C.c_int]
+    L.ctb_fingerprint.restype = C.c_uint64
+    L.ctb_fingerprint.argtypes = [vp, C.c_size_t]
     L.ctb_push_rows.restype = C.c_int
     L.ctb_push_rows.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(vp), C.c_int, vp]
     L.ctb_transform.restype = C.c_int

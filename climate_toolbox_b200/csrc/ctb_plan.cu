@@ -887,3 +887,25 @@ extern "C" int ctb_pull_pack(const ctb_plan* P, const void* x, int dtype, int64_
   CTB_LAUNCH_CHECK();
   return CTB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Fingerprint of a host buffer for the plan cache's fast path: 8 independent polynomial lanes
+// h_j = h_j * P + word (mod 2^64, P odd) over the 64-bit words j, j+8, ..., folded with a second
+// multiplier.  Editing a word, or swapping two different words, changes the value; the length is mixed in.
+extern "C" uint64_t ctb_fingerprint(const void* data, size_t nbytes) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  constexpr uint64_t P = 0x9E3779B97F4A7C15ull, Q = 0xC2B2AE3D27D4EB4Full;
+  uint64_t h[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+  size_t n64 = nbytes / 64;
+  for (size_t i = 0; i < n64; ++i, p += 64) {
+    uint64_t w[8];
+    std::memcpy(w, p, 64);
+#pragma GCC unroll 8
+    for (int j = 0; j < 8; ++j) h[j] = h[j] * P + w[j];
+  }
+  uint64_t tail[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::memcpy(tail, p, nbytes - n64 * 64);
+  uint64_t r = (uint64_t)nbytes;
+  for (int j = 0; j < 8; ++j) r = (r ^ (h[j] * P + tail[j])) * Q + (r >> 29);
+  return r;
+}
