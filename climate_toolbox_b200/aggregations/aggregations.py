@@ -16,6 +16,7 @@ gridcell transform and ``sum(w*x)/sum(w)`` run as one fused CUDA kernel
 from __future__ import annotations
 
 import functools
+import os
 
 import numpy as np
 import pandas as pd
@@ -581,8 +582,16 @@ def weighted_aggregate_grid_to_regions_multi(ds, variable, aggwts, agglev, weigh
     return to_like(out, like)
 
 
+def _weights_cache_file(weights_file, cache_dir):
+    """Path of the parsed-frame cache of a weights CSV: keyed by absolute path, size and mtime."""
+    import hashlib
+    st = os.stat(weights_file)
+    key = "{}|{}|{}".format(os.path.abspath(weights_file), st.st_size, st.st_mtime_ns)
+    return os.path.join(cache_dir, "ctb_weights_{}.feather".format(hashlib.sha1(key.encode()).hexdigest()[:20]))
+
+
 @functools.lru_cache(maxsize=8)
-def prepare_spatial_weights_data(weights_file):
+def prepare_spatial_weights_data(weights_file, cache_dir=None):
     """
     Rescales the pix_cent_x column values (reference ``aggregations.py:127-152``).
 
@@ -591,8 +600,28 @@ def prepare_spatial_weights_data(weights_file):
     duplicates are KEPT (the reference's ``drop_duplicates()`` discards its
     result); columns renamed to ``lon`` / ``lat``; index named ``reshape_index``.
     Memoised per path like the reference's ``toolz.memoize``.
+
+    ``cache_dir`` (or the environment variable ``CTB_WEIGHTS_CACHE``): the parsed frame
+    is also kept on disk in Arrow IPC format, keyed by the CSV's path, size and modification time,
+    so that the next PROCESS skips the CSV parse (a segment-weights file of 420k rows: seconds of
+    ``read_csv`` against tens of milliseconds).  The device plan is rebuilt from the frame
+    (``_engine.get_plan``: one-time, ~0.15 s) and cached by content in the process.
     """
+    cache_dir = cache_dir or os.environ.get("CTB_WEIGHTS_CACHE")
+    cached = None
+    if cache_dir:
+        cached = _weights_cache_file(weights_file, cache_dir)
+        if os.path.exists(cached):
+            df = pd.read_feather(cached)
+            df.index.names = ["reshape_index"]
+            return df
     df = pd.read_csv(weights_file)
     df.loc[df["pix_cent_x"] == 180.125, "pix_cent_x"] = -179.875
     df.index.names = ["reshape_index"]
-    return df.rename(columns={"pix_cent_x": "lon", "pix_cent_y": "lat"})
+    df = df.rename(columns={"pix_cent_x": "lon", "pix_cent_y": "lat"})
+    if cached:
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = "{}.{}.tmp".format(cached, os.getpid())
+        df.reset_index(drop=True).to_feather(tmp)
+        os.replace(tmp, cached)       # atomic: concurrent ranks may race to write the same file
+    return df

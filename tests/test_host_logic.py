@@ -244,3 +244,35 @@ def test_growing_season_mask_matches_oracle():
                                   np.nan_to_num(ref[3:7][:, ::-1][:, :5], nan=-1))
     with pytest.raises(KeyError):
         get_daily_growing_season_mask(lat + 0.01, lon[order], time, gd)
+
+
+def test_weights_csv_disk_cache_round_trip(tmp_path):
+    """SURVEY 8-f2: the parsed weights frame persists across processes (Arrow IPC next to nothing else);
+    the cached frame equals the parsed one, and a rewritten CSV is parsed again."""
+    import time
+
+    from climate_toolbox_b200.aggregations import aggregations as A
+    rng = np.random.default_rng(0)
+    n = 500
+    csv = pd.DataFrame({"pix_cent_x": rng.choice([-179.875, 0.125, 180.125], n), "pix_cent_y": rng.normal(size=n),
+                        "hierid": ["R%03d" % i for i in rng.integers(0, 40, n)], "popwt": rng.random(n),
+                        "areawt": rng.random(n)})
+    p = tmp_path / "w.csv"
+    csv.to_csv(p, index=False)
+    cache = tmp_path / "cache"
+    A.prepare_spatial_weights_data.cache_clear()
+    a = A.prepare_spatial_weights_data(str(p), cache_dir=str(cache))
+    files = list(cache.iterdir())
+    assert len(files) == 1 and files[0].suffix == ".feather"
+    A.prepare_spatial_weights_data.cache_clear()          # "next process"
+    b = A.prepare_spatial_weights_data(str(p), cache_dir=str(cache))
+    pd.testing.assert_frame_equal(a, b)
+    assert b.index.name == "reshape_index" and not (b["lon"] == 180.125).any()
+    plain = oracle.prepare_spatial_weights_data(str(p))
+    pd.testing.assert_frame_equal(b.reset_index(drop=True), plain.reset_index(drop=True), check_dtype=False)
+    # a rewritten file has another key
+    time.sleep(0.01)
+    csv.iloc[:10].to_csv(p, index=False)
+    A.prepare_spatial_weights_data.cache_clear()
+    c = A.prepare_spatial_weights_data(str(p), cache_dir=str(cache))
+    assert len(c) == 10 and len(list(cache.iterdir())) == 2
