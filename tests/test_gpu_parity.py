@@ -963,3 +963,32 @@ def test_randomized_parity(seed):
     # (W = half the daily range, here <= max|spread|), so W joins the scale of the 1e-9 test
     scale = scale + (np.abs(spread).max() if kind in ("edd", "gdd") else 0.0)
     check(got_v, ref, scale)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_push_rows_copies_the_column_block(engine):
+    """ctb_push_rows (the multi-GPU gather as a push) on one GPU: the "peers" are two more buffers of this
+    device.  The column block arrives bit-exact, everything else stays untouched, the source is skipped."""
+    import ctypes as C
+
+    from climate_toolbox_b200 import _engine as E
+    from climate_toolbox_b200 import _native as N
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    n_rows, ld, t0, n = 997, 1460, 183, 181
+    src = torch.randn((n_rows, ld), generator=g, device=dev, dtype=torch.float64)
+    peers = [torch.full((n_rows, ld), -7.0, device=dev, dtype=torch.float64) for _ in range(2)]
+    keep = src.clone()
+    arr = (C.c_void_p * 3)(peers[0].data_ptr(), src.data_ptr(), peers[1].data_ptr())
+    N.check(N.lib().ctb_push_rows(C.c_void_p(src.data_ptr()), ld, t0, n, n_rows, 3, arr, engine, E._stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(src, keep)
+    for p in peers:
+        assert torch.equal(p[:, t0:t0 + n], src[:, t0:t0 + n])
+        assert bool((p[:, :t0] == -7.0).all()) and bool((p[:, t0 + n:] == -7.0).all())
+    # a block wider than one pass of the copy kernel (256 columns per warp and pass), odd sizes
+    wide = torch.zeros((5, ld), device=dev, dtype=torch.float64)
+    arr1 = (C.c_void_p * 1)(wide.data_ptr())
+    N.check(N.lib().ctb_push_rows(C.c_void_p(src.data_ptr()), ld, 3, 777, 5, 1, arr1, engine, E._stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(wide[:, 3:780], src[:5, 3:780]) and float(wide[:, 780:].abs().sum()) == 0.0
