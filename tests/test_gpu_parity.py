@@ -992,3 +992,31 @@ def test_push_rows_copies_the_column_block(engine):
     N.check(N.lib().ctb_push_rows(C.c_void_p(src.data_ptr()), ld, 3, 777, 5, 1, arr1, engine, E._stream_ptr(dev)))
     torch.cuda.synchronize()
     assert torch.equal(wide[:, 3:780], src[:5, 3:780]) and float(wide[:, 780:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("kind,params,n_out", [("identity", (), 1), ("poly", (273.15, 1, 2), 2)])
+def test_fused_peer_epilogue_on_one_gpu(kind, params, n_out):
+    """The gather fused into the kernel's epilogue (ctb_agg_opts.peer_out / peer_row), driven on ONE GPU: the
+    "peers" are two buffers of this device.  Both receive what the plain launch writes -- rows permuted by
+    peer_row, columns offset like a time shard -- including the split regions the fix-up kernel finishes."""
+    from climate_toolbox_b200 import _engine as E
+    from climate_toolbox_b200 import _native as N
+    lat, lon, df, tas, _, _ = _config(1.0, 300, 70, seed=9)
+    df = df.copy()
+    df.loc[df.index[:4000], "hierid"] = df["hierid"].iloc[0]        # one region larger than a tile: split rows
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(tas).to(dev).view(tas.shape[0], -1)
+    T, ncell = x.shape
+    plan = E.get_plan(E.GridSpec(lat, lon), df, "popwt", "hierid", device=dev)
+    ref = E.aggregate_device(plan, x, None, N.LAYOUT_TIME_MAJOR, ncell, None, T, kind, params, n_out)
+    t_total, t0 = T + 37, 21                                           # this "rank" owns days [21, 21 + T)
+    bufs = [torch.full((n_out, plan.R, t_total), -5.0, device=dev, dtype=torch.float64) for _ in range(2)]
+    row = torch.as_tensor(plan.region_order(), device=dev)
+    E.aggregate_device(plan, x, None, N.LAYOUT_TIME_MAJOR, ncell, None, T, kind, params, n_out,
+                       out=E._OffsetOut(bufs[0], t0), out_ld=t_total,
+                       peer_ptrs=[b.data_ptr() + 8 * t0 for b in bufs], peer_row=row)
+    torch.cuda.synchronize()
+    for b in bufs:
+        got = b.index_select(1, row.to(torch.int64))[:, :, t0:t0 + T]
+        assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(ref))
+        assert bool((b[:, :, :t0] == -5.0).all()) and bool((b[:, :, t0 + T:] == -5.0).all())
