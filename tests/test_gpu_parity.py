@@ -1020,3 +1020,22 @@ def test_fused_peer_epilogue_on_one_gpu(kind, params, n_out):
         got = b.index_select(1, row.to(torch.int64))[:, :, t0:t0 + T]
         assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(ref))
         assert bool((b[:, :, :t0] == -5.0).all()) and bool((b[:, :, t0 + T:] == -5.0).all())
+
+
+def test_ipc_buffer_alloc_and_free():
+    """ctb_ipc_alloc hands out device memory + a 64-byte handle for the other ranks; the owner frees it.
+    (Opening a handle needs a second process: __graft_entry__.smoke() and bench.py --gpus N do that.)"""
+    import ctypes as C
+
+    from climate_toolbox_b200 import _native as N
+    from climate_toolbox_b200.parallel import _tensor_from_ptr
+    ptr = C.c_void_p()
+    handle = (C.c_ubyte * N.IPC_HANDLE_BYTES)()
+    N.check(N.lib().ctb_ipc_alloc(8 * 1000, 0, C.byref(ptr), handle))
+    assert ptr.value and any(handle)
+    t = _tensor_from_ptr(ptr.value, (10, 100), torch.device("cuda", 0), None)
+    t.copy_(torch.arange(1000, dtype=torch.float64, device="cuda").view(10, 100))
+    assert float(t.sum()) == 999 * 1000 / 2
+    del t
+    torch.cuda.synchronize()
+    N.check(N.lib().ctb_ipc_free(ptr, 0))
