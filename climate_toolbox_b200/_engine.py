@@ -76,6 +76,7 @@ class Plan:
         N.check(N.lib().ctb_plan_get_info(self._h, C.byref(info)))
         self.info = info.as_dict()
         self._tix_cache = {}
+        self._ws_cache = {}
 
     R = property(lambda s: s.info["n_regions"])
     compact = property(lambda s: s.info["n_packed_cells"] > 0)
@@ -302,9 +303,20 @@ def get_time_groups(group_of_day, device=None):
     return hit
 
 
+_PARAMS_CACHE = {}
+
+
 def _params_array(kind, params):
-    a = np.ascontiguousarray(params, dtype=np.float64)
-    return a, (_dp(a) if a.size else None)
+    """(float64 array, ctypes pointer) of a transform's parameters; cached: the launch path of a small
+    problem (config 1: a 10 us kernel) is host-bound."""
+    key = (kind, tuple(float(p) for p in params))
+    hit = _PARAMS_CACHE.get(key)
+    if hit is None:
+        a = np.ascontiguousarray(params, dtype=np.float64)
+        if len(_PARAMS_CACHE) > 64:
+            _PARAMS_CACHE.clear()
+        hit = _PARAMS_CACHE[key] = (a, (_dp(a) if a.size else None))
+    return hit
 
 
 def _stream_ptr(device, stream=None):
@@ -313,12 +325,19 @@ def _stream_ptr(device, stream=None):
 
 
 def _workspace(plan, T, n_out, layout, variant, groups, workspace):
-    L = N.lib()
     staged = (variant & 0xff) != N.VARIANT_DIRECT and layout == N.LAYOUT_TIME_MAJOR
-    if groups is not None:
-        ws_bytes = L.ctb_aggregate_grouped_workspace_bytes(plan._h, groups._h, n_out)
-    else:
-        ws_bytes = L.ctb_aggregate_workspace_bytes(plan._h, T, n_out) if staged else 0
+    key = (int(T), int(n_out), staged)
+    ws_bytes = plan._ws_cache.get(key) if groups is None else None
+    if ws_bytes is None:
+        L = N.lib()
+        if groups is not None:
+            ws_bytes = L.ctb_aggregate_grouped_workspace_bytes(plan._h, groups._h, n_out)
+        else:
+            ws_bytes = L.ctb_aggregate_workspace_bytes(plan._h, T, n_out) if staged else 0
+        if groups is None:
+            if len(plan._ws_cache) > 64:
+                plan._ws_cache.clear()
+            plan._ws_cache[key] = ws_bytes
     if ws_bytes and (workspace is None or workspace.numel() * 8 < ws_bytes):
         workspace = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=plan.device)
     return workspace
