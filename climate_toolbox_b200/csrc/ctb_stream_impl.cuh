@@ -38,6 +38,10 @@
 
 namespace {
 
+#ifndef CTB_STICKY_ALL
+#define CTB_STICKY_ALL 1   // 0: only the single-output kernels skip the widening after a failed range check
+#endif
+
 // CTB_NP / CTB_WAIT_NS / CTB_PACE_NS / CTB_STAGES / CTB_TILE_UNITS_OVERRIDE: compile-time knobs of the
 // bench_micro/ experiments (profiles/micro/r2_stream_sweeps.md); the defaults are the measured best
 #ifdef CTB_NP
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_stream_kernel(const AggArgs a)
           // widening's range check in nearly every region-tile: after a failure the warp goes straight
           // to the exact loop and only probes the fast one every 8th region (measured: 0.70 -> 0.60 ms for
           // such data, 0.60 for positive data either way -- bench_micro/sign_cost.py)
-          if (!skip_fast || (++probe & 7) == 0) {
+          if (!(CTB_STICKY_ALL || NOUT == 1) || !skip_fast || (++probe & 7) == 0) {
             done = reduce_region_widen<KIND, NOUT, GATE>(a.tr, tile_a, ea, nq, lane, doy, v);
             skip_fast = !done;
           }
